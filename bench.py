@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark (contract in the task statement; layout in DESIGN.md section 5).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extras]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = Correlation forward + backward (both input gradients) at BASELINE.json configs[1]:
+fp32 [8,256,112,256] per GPU, pad=20,k=1,md=20,s1=1,s2=2 (D=441).  Weak scaling: every rank owns
+its own 8-sample shard, no data-path collective (the layers are per-sample).
+
+metric/value : algorithmic GB/s of fwd+bwd (read each input once + write each output once,
+               2 218 524 672 B per 8-sample step) summed over ranks, inputs resident in HBM.
+e2e          : same metric with HOST buffers: every step copies f1,f2,gradOutput from pinned host
+               memory and copies output,gradInput1,gradInput2 back (through the module-level API).
+roofline     : the dominant kernel (correlation backward) timed alone with CUDA events; achieved =
+               its algorithmic bytes per launch / its duration, against MEASURED_PEAKS.json's HBM GB/s.
+cpu_baseline : the CPU oracle (oracle/oracle.c, a port -- the reference has no CPU path) on a 1-sample
+               slice of the same workload, all host cores.
+--impl reference: the reference's OWN CUDA kernels rebuilt for sm_100a (oracle/_ref) on the same
+               workload on the same GPU; if they are not built, the CPU oracle port instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(B=8, C=256, H=112, W=256, pad=20, k=1, md=20, s1=1, s2=2)
+D = 441
+
+
+def alg_bytes(B):
+    """fwd 4*(2*B*C*H*W + B*D*oH*oW); bwd 4*(B*D*oH*oW + 4*B*C*H*W)."""
+    chw = CFG["C"] * CFG["H"] * CFG["W"]
+    dhw = D * CFG["H"] * CFG["W"]
+    fwd = 4 * (2 * B * chw + B * dhw)
+    bwd = 4 * (B * dhw + 4 * B * chw)
+    bwd_launch = 4 * (B * dhw + 2 * B * chw)     # one gradInput: gradOutput + other input + output
+    return fwd, bwd, bwd_launch
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        rows = [l for (t, l) in self.lines if t0 <= t <= t1] or [l for (_, l) in self.lines[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+def time_loop(fn, steps, warmup, sync, dist_barrier=None):
+    """W untimed + K timed calls of fn() between CUDA events on the current stream."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    if dist_barrier:
+        dist_barrier()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    sync()
+    if dist_barrier:
+        dist_barrier()
+    t1 = time.time()
+    return e0.elapsed_time(e1), t0, t1
+
+
+def time_cold(fn, iters, flush):
+    """Per-iteration event timing with an L2 flush (write > L2 bytes) before each call."""
+    import torch
+    ms = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms.sort()
+    return ms[len(ms) // 2]
+
+
+def cpu_baseline_sample():
+    """CPU oracle port on ONE sample of the workload (1/8 step), all host cores."""
+    import numpy as np
+    from oracle import cpu as orc
+    rng = np.random.RandomState(0)
+    shp = (1, CFG["C"], CFG["H"], CFG["W"])
+    a, b = rng.randn(*shp).astype(np.float32), rng.randn(*shp).astype(np.float32)
+    prm = (CFG["pad"], CFG["k"], CFG["md"], CFG["s1"], CFG["s2"])
+    orc.correlation_forward(a[:, :8, :8, :16], b[:, :8, :8, :16], *prm)   # build + warm
+    t0 = time.time()
+    out = orc.correlation_forward(a, b, *prm)
+    go = rng.randn(*out.shape).astype(np.float32)
+    t1 = time.time()
+    orc.correlation_backward(a, b, go, *prm)
+    t2 = time.time()
+    fwd, bwd, _ = alg_bytes(1)
+    secs = (t1 - t0) + (t2 - t1)
+    return {"value": round((fwd + bwd) / secs / 1e9, 4), "unit": "GB/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "1 of 8 samples of the cfg2 step (fwd %.2fs + bwd %.2fs), OpenMP on all cores" % (t1 - t0, t2 - t1)}
+
+
+def build_impl(impl, dev):
+    """Returns (name, fwd(f1,f2,out), bwd(f1,f2,gO,g1,g2), launches()) for the chosen arm."""
+    import torch
+    prm = (CFG["pad"], CFG["k"], CFG["md"], CFG["s1"], CFG["s2"])
+    if impl == "ours":
+        import flownet2_b200
+        F2 = flownet2_b200.functional
+
+        def fwd(a, b, out):
+            F2.correlation_forward(a, b, *prm, 1, out=out)
+
+        def bwd(a, b, go, g1, g2):
+            F2.correlation_backward(a, b, go, *prm, 1, out1=g1, out2=g2)
+        return "ours", fwd, bwd, F2.launch_count
+    from oracle import ref as oref
+    ext = oref.load_extension("correlation_cuda")
+    if ext is None:
+        return None, None, None, None
+    scratch = [torch.empty(0, device=dev) for _ in range(2)]
+    count = [0]
+
+    def fwd(a, b, out):
+        ext.forward(a, b, scratch[0], scratch[1], out, *prm, 1)
+        count[0] += 3
+
+    def bwd(a, b, go, g1, g2):
+        ext.backward(a, b, scratch[0], scratch[1], go, g1, g2, *prm, 1)
+        count[0] += 2 + 2 * a.shape[0]
+    return "reference-cuda", fwd, bwd, lambda: count[0]
+
+
+def extras_ours(dev, flush):
+    """cfg3 Resample2d / ChannelNorm kernels (cold-L2 median, GB/s of algorithmic bytes) and the true
+    FlowNet2 correlation shape.  Outside the headline timed region."""
+    import torch
+    import flownet2_b200
+    F2 = flownet2_b200.functional
+    peak, _ = measured_peak()
+    res = {}
+    g = torch.Generator(device=dev).manual_seed(0)
+    B, H, W = 8, 448, 1024
+    img = torch.rand(B, 3, H, W, device=dev, generator=g)
+    flow = torch.randn(B, 2, H, W, device=dev, generator=g) * 4
+    go3 = torch.randn(B, 3, H, W, device=dev, generator=g)
+    out3, gimg, gflow = torch.empty_like(img), torch.empty_like(img), torch.empty_like(flow)
+    hw = B * H * W * 4
+
+    def rec(name, fn, nbytes, iters=15):
+        fn()
+        ms = time_cold(fn, iters, flush)
+        res[name] = {"ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1), "frac_hbm": round(nbytes / ms / 1e6 / peak, 3)}
+
+    rec("resample2d_fwd", lambda: F2.resample2d_forward(img, flow, out=out3), hw * (3 + 3 + 2))
+    rec("resample2d_bwd", lambda: F2.resample2d_backward(img, flow, go3, out1=gimg, out2=gflow), hw * (3 * 3 + 2 * 2))
+    for C in (3, 2):
+        x = torch.randn(B, C, H, W, device=dev, generator=g)
+        o = torch.empty(B, 1, H, W, device=dev)
+        gi = torch.empty_like(x)
+        gon = torch.randn(B, 1, H, W, device=dev, generator=g)
+        rec("channelnorm_fwd_c%d" % C, lambda: F2.channelnorm_forward(x, out=o), hw * (C + 1))
+        rec("channelnorm_bwd_c%d" % C, lambda: F2.channelnorm_backward(x, o, gon, out=gi), hw * (2 * C + 2))
+    # correlation at the shape FlowNet2 really produces at 448x1024
+    a = torch.randn(8, 256, 56, 128, device=dev, generator=g)
+    b = torch.randn(8, 256, 56, 128, device=dev, generator=g)
+    o = torch.empty(8, 441, 56, 128, device=dev)
+    gO = torch.randn(8, 441, 56, 128, device=dev, generator=g)
+    g1, g2 = torch.empty_like(a), torch.empty_like(b)
+    rec("correlation_fwd_56x128", lambda: F2.correlation_forward(a, b, 20, 1, 20, 1, 2, out=o), 218595328)
+    rec("correlation_bwd_56x128", lambda: F2.correlation_backward(a, b, gO, 20, 1, 20, 1, 2, out1=g1, out2=g2), 336035840)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    name, fwd, bwd, launches = build_impl(args.impl, dev)
+    cpu_only_reference = args.impl == "reference" and name is None
+    if cpu_only_reference:
+        # reference kernels not built: the arm is the CPU oracle port, rank 0 only
+        if rank == 0:
+            cb = cpu_baseline_sample()
+            line = {"impl": "reference", "metric": "correlation_fwd_bwd_algorithmic_GBps", "value": cb["value"],
+                    "unit": "GB/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": None,
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                    "data": "synthetic", "config": {"workload": "cfg2 correlation fwd+bwd, 1-sample CPU slice"},
+                    "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0,
+                                                "d2h_bytes_per_step": 0}}
+            print(json.dumps(line))
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    B = CFG["B"]
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    shp = (B, CFG["C"], CFG["H"], CFG["W"])
+    f1 = torch.randn(*shp, device=dev, generator=g)
+    f2 = torch.randn(*shp, device=dev, generator=g)
+    out = torch.empty(B, D, CFG["H"], CFG["W"], device=dev)
+    gO = torch.randn(B, D, CFG["H"], CFG["W"], device=dev, generator=g)
+    g1, g2 = torch.empty_like(f1), torch.empty_like(f2)
+
+    def sync():
+        torch.cuda.synchronize()
+
+    def barrier():
+        if dist:
+            dist.barrier()
+
+    def step():
+        fwd(f1, f2, out)
+        bwd(f1, f2, gO, g1, g2)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K, Wm = args.steps, args.warmup
+    if args.impl == "reference":
+        K = min(K, 5)            # the reference backward takes ~0.5 s per step
+        Wm = 3
+    l0 = launches()
+    ms, t0, t1 = time_loop(step, K, Wm, sync, barrier if dist else None)
+    l1 = launches()
+    launches_timed = (l1 - l0) * K // (K + Wm) if args.impl == "ours" else (l1 - l0) * K // (K + Wm)
+    clocks = sampler.window(t0, t1) if rank == 0 else None
+
+    # dominant-kernel timing (alone, same stream): forward kernel, backward kernels
+    ms_f, _, _ = time_loop(lambda: fwd(f1, f2, out), K, 2, sync)
+    ms_b, _, _ = time_loop(lambda: bwd(f1, f2, gO, g1, g2), K, 2, sync)
+
+    # end-to-end through host buffers
+    hf1, hf2, hgO = (torch.empty(t.shape, pin_memory=True).copy_(t) for t in (f1, f2, gO))
+    hout, hg1, hg2 = (torch.empty(t.shape, pin_memory=True) for t in (out, g1, g2))
+    h2d = sum(t.numel() * 4 for t in (hf1, hf2, hgO))
+    d2h = sum(t.numel() * 4 for t in (hout, hg1, hg2))
+
+    def e2e_step():
+        f1.copy_(hf1, non_blocking=True)
+        f2.copy_(hf2, non_blocking=True)
+        gO.copy_(hgO, non_blocking=True)
+        step()
+        hout.copy_(out, non_blocking=True)
+        hg1.copy_(g1, non_blocking=True)
+        hg2.copy_(g2, non_blocking=True)
+    Ke = min(K, 10)
+    ms_e, _, _ = time_loop(e2e_step, Ke, 2, sync, barrier if dist else None)
+
+    stats = torch.tensor([ms, ms_e / Ke * K], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms, ms_e_scaled = float(stats[0]), float(stats[1])
+
+    fwd_b, bwd_b, bwd_launch_b = alg_bytes(B)
+    total_b = (fwd_b + bwd_b) * world
+    value = total_b * K / (ms * 1e-3) / 1e9
+    e2e_value = total_b * K / (ms_e_scaled * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+
+    if rank == 0:
+        per_f, per_b = ms_f / K, ms_b / K
+        dominant = "correlation_backward" if per_b >= per_f else "correlation_forward"
+        if dominant == "correlation_backward":
+            launch_ms = per_b / (2 if args.impl == "ours" else 1)
+            ach = (bwd_launch_b if args.impl == "ours" else bwd_b) / (launch_ms * 1e-3) / 1e9
+        else:
+            launch_ms = per_f
+            ach = fwd_b / (per_f * 1e-3) / 1e9
+        line = {
+            "metric": "correlation_fwd_bwd_algorithmic_GBps", "value": round(value, 2), "unit": "GB/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Correlation(pad=20,k=1,md=20,s1=1,s2=2) fwd+bwd on fp32 [8,256,112,256] per GPU "
+                                   "(BASELINE configs[1])", "per_gpu_batch": B, "global_batch": B * world,
+                       "l2": "inputs+outputs 1.28 GB per step >> 126 MB L2 (no flush needed)",
+                       "parallelism": "replicas x%d (weak, no data-path collective)" % world, "impl": name},
+            "frac_hbm_peak": round(value / world / peak, 4),
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "launch_ms": round(launch_ms, 4),
+                         "note": "correlation is FP32-FMA-bound at this shape (59/77 FLOP/B); see DESIGN.md",
+                         "fp32_tflops": round((51.79e9 * 3) / ((per_f + per_b) * 1e-3) / 1e12, 2)},
+            "kernels": {"forward_ms": round(per_f, 4), "backward_ms": round(per_b, 4),
+                        "forward_GBps": round(fwd_b / per_f / 1e6, 1), "backward_GBps": round(bwd_b / per_b / 1e6, 1)},
+            "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(ms_e_scaled / K, 3), "steps": Ke},
+            "gpu_launches": int(launches_timed),
+            "clocks": clocks,
+        }
+        if args.impl == "reference":
+            line["impl"] = "reference"
+            line["config"]["impl"] = "reference CUDA kernels rebuilt for sm_100a (oracle/_ref)"
+        if world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline_sample()
+            except Exception as e:
+                line["cpu_baseline"] = {"error": str(e)[:200]}
+        if args.impl == "ours" and not args.no_extras and world == 1:
+            try:
+                flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+                del hf1, hf2, hgO, hout, hg1, hg2
+                line["ops"] = extras_ours(dev, flush)
+            except Exception as e:
+                line["ops"] = {"error": str(e)[:300]}
+        print(json.dumps(line))
+    sampler.stop()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,155 @@
+// channelnorm.cu -- per-pixel L2 norm over channels, forward and backward (HBM-streaming).
+//
+// Replaces kernel_channelnorm_update_output / kernel_channelnorm_backward_input1
+// (reference channelnorm_package/channelnorm_kernel.cu:18-60, :63-96).
+//
+// B200 design: pure streaming, 0.2-0.5 FLOP/B -> HBM-bound.  One thread owns 4 consecutive pixels:
+// C independent 128-bit read-once loads (L1 no-allocate) are issued back to back before any use,
+// so each SM keeps >= 2048 thr x C x 16 B in flight (enough for ~6.6 TB/s at ~600 ns latency),
+// then one 128-bit store.  No shared memory, no pre-zeroed outputs (the reference zero-fills
+// them first, channelnorm.py:11,23: 2x the write traffic).
+#include "common.cuh"
+
+namespace fn2 {
+
+template <int CT>  // CT > 0: compile-time channel count; CT == 0: runtime loop
+__global__ void __launch_bounds__(256)
+channelnorm_fwd_v4(const float *__restrict__ in, float *__restrict__ out, int C, int hw4, long n4) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n4) return;
+    int b = (int)(idx / hw4);
+    int p = (int)(idx - (long)b * hw4);
+    const int Cn = CT > 0 ? CT : C;
+    const float *src = in + ((long)b * Cn * hw4 + p) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (CT > 0) {
+        float4 v[CT > 0 ? CT : 1];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) v[c] = ldg_stream4(src + (long)c * hw4 * 4);
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {  // channel order = the reference's accumulation order
+            acc.x += v[c].x * v[c].x; acc.y += v[c].y * v[c].y;
+            acc.z += v[c].z * v[c].z; acc.w += v[c].w * v[c].w;
+        }
+    } else {
+        for (int c = 0; c < Cn; ++c) {
+            float4 v = ldg_stream4(src + (long)c * hw4 * 4);
+            acc.x += v.x * v.x; acc.y += v.y * v.y; acc.z += v.z * v.z; acc.w += v.w * v.w;
+        }
+    }
+    float4 r = make_float4(sqrtf(acc.x), sqrtf(acc.y), sqrtf(acc.z), sqrtf(acc.w));
+    stg_stream4(out + idx * 4, r);
+}
+
+__global__ void __launch_bounds__(256)
+channelnorm_fwd_scalar(const float *__restrict__ in, float *__restrict__ out, int C, int hw, long n) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    int b = (int)(idx / hw);
+    int p = (int)(idx - (long)b * hw);
+    const float *src = in + (long)b * C * hw + p;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) {
+        float v = __ldg(src + (long)c * hw);
+        acc += v * v;
+    }
+    out[idx] = sqrtf(acc);
+}
+
+// gI = gO * in / (out + 1e-9).  The reference's divide is promoted to double by the 1e-9 literal
+// (channelnorm_kernel.cu:92-94); fp32 here differs by <= 1 ulp-level relative error (~1e-7),
+// far inside the 1e-4 contract, and out == 0 still yields gO*0/1e-9 = 0.
+__device__ __forceinline__ float cn_bwd(float g, float x, float o) { return g * x / (o + 1e-9f); }
+
+template <int CT>
+__global__ void __launch_bounds__(256)
+channelnorm_bwd_v4(const float *__restrict__ in, const float *__restrict__ out,
+                   const float *__restrict__ gout, float *__restrict__ gin, int C, int hw4, long n4) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n4) return;
+    int b = (int)(idx / hw4);
+    int p = (int)(idx - (long)b * hw4);
+    const int Cn = CT > 0 ? CT : C;
+    const long base = ((long)b * Cn * hw4 + p) * 4;
+    float4 o = ldg_stream4(out + idx * 4);
+    float4 g = ldg_stream4(gout + idx * 4);
+    if (CT > 0) {
+        float4 v[CT > 0 ? CT : 1];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) v[c] = ldg_stream4(in + base + (long)c * hw4 * 4);
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            float4 r = make_float4(cn_bwd(g.x, v[c].x, o.x), cn_bwd(g.y, v[c].y, o.y),
+                                   cn_bwd(g.z, v[c].z, o.z), cn_bwd(g.w, v[c].w, o.w));
+            stg_stream4(gin + base + (long)c * hw4 * 4, r);
+        }
+    } else {
+        for (int c = 0; c < Cn; ++c) {
+            float4 v = ldg_stream4(in + base + (long)c * hw4 * 4);
+            float4 r = make_float4(cn_bwd(g.x, v.x, o.x), cn_bwd(g.y, v.y, o.y),
+                                   cn_bwd(g.z, v.z, o.z), cn_bwd(g.w, v.w, o.w));
+            stg_stream4(gin + base + (long)c * hw4 * 4, r);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+channelnorm_bwd_scalar(const float *__restrict__ in, const float *__restrict__ out,
+                       const float *__restrict__ gout, float *__restrict__ gin, int C, int hw, long n) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    int b = (int)(idx / hw);
+    int p = (int)(idx - (long)b * hw);
+    float o = __ldg(out + idx), g = __ldg(gout + idx);
+    for (int c = 0; c < C; ++c) {
+        long i = ((long)b * C + c) * hw + p;
+        gin[i] = cn_bwd(g, __ldg(in + i), o);
+    }
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int channelnorm_forward(const float *in, float *out, int B, int C, int H, int W, cudaStream_t st) {
+    const int hw = H * W;
+    const int T = 256;
+    if (hw % 4 == 0 && aligned16(in) && aligned16(out)) {
+        long n4 = (long)B * (hw / 4);
+        unsigned grid = (unsigned)((n4 + T - 1) / T);
+        switch (C) {
+            case 1: channelnorm_fwd_v4<1><<<grid, T, 0, st>>>(in, out, C, hw / 4, n4); break;
+            case 2: channelnorm_fwd_v4<2><<<grid, T, 0, st>>>(in, out, C, hw / 4, n4); break;
+            case 3: channelnorm_fwd_v4<3><<<grid, T, 0, st>>>(in, out, C, hw / 4, n4); break;
+            case 4: channelnorm_fwd_v4<4><<<grid, T, 0, st>>>(in, out, C, hw / 4, n4); break;
+            default: channelnorm_fwd_v4<0><<<grid, T, 0, st>>>(in, out, C, hw / 4, n4); break;
+        }
+    } else {
+        long n = (long)B * hw;
+        channelnorm_fwd_scalar<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(in, out, C, hw, n);
+    }
+    count_launch();
+    return check_launch("channelnorm_forward");
+}
+
+int channelnorm_backward(const float *in, const float *out, const float *gout, float *gin, int B,
+                         int C, int H, int W, cudaStream_t st) {
+    const int hw = H * W;
+    const int T = 256;
+    if (hw % 4 == 0 && aligned16(in) && aligned16(out) && aligned16(gout) && aligned16(gin)) {
+        long n4 = (long)B * (hw / 4);
+        unsigned grid = (unsigned)((n4 + T - 1) / T);
+        switch (C) {
+            case 1: channelnorm_bwd_v4<1><<<grid, T, 0, st>>>(in, out, gout, gin, C, hw / 4, n4); break;
+            case 2: channelnorm_bwd_v4<2><<<grid, T, 0, st>>>(in, out, gout, gin, C, hw / 4, n4); break;
+            case 3: channelnorm_bwd_v4<3><<<grid, T, 0, st>>>(in, out, gout, gin, C, hw / 4, n4); break;
+            case 4: channelnorm_bwd_v4<4><<<grid, T, 0, st>>>(in, out, gout, gin, C, hw / 4, n4); break;
+            default: channelnorm_bwd_v4<0><<<grid, T, 0, st>>>(in, out, gout, gin, C, hw / 4, n4); break;
+        }
+    } else {
+        long n = (long)B * hw;
+        channelnorm_bwd_scalar<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(in, out, gout, gin, C, hw, n);
+    }
+    count_launch();
+    return check_launch("channelnorm_backward");
+}
+
+}  // namespace fn2

@@ -1,0 +1,110 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/fn2b200.h declares, and validates its arguments (no kernel is launched here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "fn2b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(fn2b200_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    import flownet2_b200
+    lib = ctypes.CDLL(flownet2_b200._lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 11
+    for name in declared:
+        assert hasattr(lib, name), "libfn2b200.so does not export %s" % name
+    assert sorted(flownet2_b200._lib.SYMBOLS) == declared
+    assert lib.fn2b200_version() == 100
+
+
+def test_library_is_sm100a_with_tma():
+    import subprocess
+    import flownet2_b200
+    try:
+        out = subprocess.run(["cuobjdump", "-lelf", flownet2_b200._lib.LIB_PATH], capture_output=True, text=True).stdout
+    except FileNotFoundError:
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in out
+
+
+def test_argument_validation_without_gpu():
+    from flownet2_b200._lib import LIB
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)  # never dereferenced: validation fails first
+    # stride1 != 1 in backward: the reference cannot run it either
+    rc = LIB.fn2b200_correlation_backward(one, one, one, one, one, 1, 4, 8, 8, 4, 1, 4, 2, 2, 1, null)
+    assert rc == -2 and b"stride1" in LIB.fn2b200_last_error()
+    # empty output
+    rc = LIB.fn2b200_correlation_forward(one, one, one, 1, 4, 8, 8, 0, 1, 20, 1, 2, 1, null)
+    assert rc == -1
+    # null pointers
+    rc = LIB.fn2b200_correlation_forward(null, one, one, 1, 4, 8, 8, 4, 1, 4, 1, 2, 1, null)
+    assert rc == -3
+    # kernel_size > 1 for resample2d
+    st = (ctypes.c_int64 * 4)(192, 64, 8, 1)
+    rc = LIB.fn2b200_resample2d_forward(one, st, one, one, 1, 3, 8, 8, 8, 8, 2, 1, null)
+    assert rc == -2 and b"kernel_size" in LIB.fn2b200_last_error()
+    rc = LIB.fn2b200_channelnorm_forward(one, one, 1, 0, 8, 8, 2, null)
+    assert rc == -1
+    # B == 0 is a no-op success
+    assert LIB.fn2b200_channelnorm_forward(null, null, 0, 3, 8, 8, 2, null) == 0
+
+
+def test_out_shape_and_path_queries():
+    from flownet2_b200 import functional as F2
+    from flownet2_b200._lib import LIB
+    assert F2.correlation_out_shape(256, 48, 64, 20, 1, 20, 1, 2) == (441, 48, 64)
+    assert F2.correlation_out_shape(8, 12, 13, 2, 1, 4, 2, 2) == (25, 4, 5)
+    assert LIB.fn2b200_correlation_path(256, 112, 256, 20, 1, 20, 1, 2) == 1   # FlowNetC -> TMA-tiled kernels
+    assert LIB.fn2b200_correlation_path(256, 112, 256, 20, 3, 20, 1, 2) == 0   # kernel_size 3 -> generic
+    assert LIB.fn2b200_correlation_path(256, 112, 250, 20, 1, 20, 1, 2) == 0   # W % 4 != 0 -> generic
+
+
+def test_no_cpu_fallback():
+    import flownet2_b200 as f
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        f.Correlation(4, 1, 4, 1, 2, 1)(torch.zeros(1, 2, 8, 8), torch.zeros(1, 2, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        f.Resample2d()(torch.zeros(1, 3, 8, 8), torch.zeros(1, 2, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        f.ChannelNorm()(torch.zeros(1, 3, 8, 8))
+
+
+def test_api_surface_matches_reference():
+    """Constructor / Function signatures of SURVEY 8(b) level B2."""
+    import inspect
+    import flownet2_b200 as f
+    assert list(inspect.signature(f.Correlation.__init__).parameters)[1:] == [
+        "pad_size", "kernel_size", "max_displacement", "stride1", "stride2", "corr_multiply"]
+    c = f.Correlation()
+    assert (c.pad_size, c.kernel_size, c.max_displacement, c.stride1, c.stride2, c.corr_multiply) == (0, 0, 0, 1, 2, 1)
+    sig = inspect.signature(f.CorrelationFunction.forward)
+    assert [sig.parameters[k].default for k in ("pad_size", "kernel_size", "max_displacement", "stride1", "stride2",
+                                                "corr_multiply")] == [3, 3, 20, 1, 2, 1]
+    r = f.Resample2d()
+    assert (r.kernel_size, r.bilinear) == (1, True)
+    assert f.ChannelNorm().norm_deg == 2
+    assert not list(c.parameters()) and not list(c.buffers()) and not c.state_dict()
+    # B1 shim modules export exactly forward/backward
+    from flownet2_b200 import compat
+    import sys
+    compat.install_extension_shims()
+    try:
+        for name in ("correlation_cuda", "resample2d_cuda", "channelnorm_cuda"):
+            m = sys.modules[name]
+            assert callable(m.forward) and callable(m.backward)
+        assert list(inspect.signature(sys.modules["correlation_cuda"].forward).parameters) == [
+            "input1", "input2", "rInput1", "rInput2", "output", "pad_size", "kernel_size", "max_displacement",
+            "stride1", "stride2", "corr_type_multiply"]
+    finally:
+        compat.uninstall()

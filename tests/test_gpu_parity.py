@@ -1,0 +1,357 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): our sm_100a kernels, called through the C ABI,
+against the CPU oracle (oracle/oracle.c) and against the reference's own kernels (oracle/_ref).
+
+Tolerance: max|d|/max|ref| <= 1e-4 and allclose(rtol=1e-4, atol=1e-4*rms(ref)) -- the contract in
+BASELINE.json's north_star ("fp32 outputs matching the reference kernels within 1e-4 rel").
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu as orc
+from oracle import ref as oref
+from util import assert_close, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _f2():
+    import flownet2_b200
+    return flownet2_b200
+
+
+def _randn(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).float()
+
+
+# ------------------------------------------------------------------------------------------------
+# Correlation
+# ------------------------------------------------------------------------------------------------
+CORR_CASES = [
+    # (pad, k, md, s1, s2), (B, C, H, W), expected path (1 = TMA-tiled, 0 = generic)
+    ((20, 1, 20, 1, 2), (1, 256, 48, 64), 1),     # BASELINE cfg1
+    ((20, 1, 20, 1, 2), (2, 20, 13, 192), 1),     # odd H, C % 8 != 0, 1.5 tiles wide
+    ((20, 1, 20, 1, 2), (1, 3, 5, 8), 1),         # tiny: W < tile, H < row quad
+    ((20, 1, 20, 1, 2), (1, 64, 9, 260), 1),      # 3 tiles wide, ragged last tile
+    ((22, 1, 20, 1, 2), (1, 16, 10, 32), 1),      # pad > md (output larger than input), tiled
+    ((18, 1, 20, 1, 2), (1, 16, 14, 32), 1),      # pad < md (output smaller), tiled
+    ((4, 1, 4, 1, 2), (2, 7, 9, 12), 1),          # (s2, dr) = (2, 2)
+    ((8, 1, 8, 1, 2), (1, 9, 11, 16), 1),         # (2, 4)
+    ((4, 1, 4, 1, 1), (1, 5, 8, 16), 1),          # (1, 4)
+    ((3, 1, 3, 1, 1), (1, 5, 8, 8), 1),           # (1, 3): odd halo
+    ((5, 1, 5, 1, 2), (1, 6, 8, 8), 1),           # md % s2 != 0 -> dr = 2
+    ((4, 3, 4, 1, 2), (1, 6, 10, 12), 0),         # kernel_size 3 -> generic
+    ((4, 1, 4, 1, 2), (1, 6, 9, 11), 0),          # W % 4 != 0 -> generic
+    ((3, 1, 4, 1, 2), (1, 6, 9, 12), 0),          # (pad-md) odd -> oW % 4 != 0 -> generic
+    ((6, 1, 6, 1, 3), (1, 4, 9, 12), 0),          # stride2 = 3 -> generic
+]
+
+
+@pytest.mark.parametrize("params,shape,path", CORR_CASES)
+def test_correlation_vs_oracle(params, shape, path):
+    f = _f2()
+    pad, k, md, s1, s2 = params
+    B, C, H, W = shape
+    assert f._lib.LIB.fn2b200_correlation_path(C, H, W, pad, k, md, s1, s2) == path
+    a, b = _randn(shape, 10), _randn(shape, 11)
+    out = f.functional.correlation_forward(a.cuda(), b.cuda(), pad, k, md, s1, s2)
+    ref = orc.correlation_forward(a.numpy(), b.numpy(), pad, k, md, s1, s2)
+    assert_close(out.cpu().numpy(), ref, TOL, "corr fwd %s %s" % (params, shape))
+    go = _randn(ref.shape, 12)
+    g1, g2 = f.functional.correlation_backward(a.cuda(), b.cuda(), go.cuda(), pad, k, md, s1, s2)
+    r1, r2 = orc.correlation_backward(a.numpy(), b.numpy(), go.numpy(), pad, k, md, s1, s2)
+    assert_close(g1.cpu().numpy(), r1, TOL, "corr gI1 %s %s" % (params, shape))
+    assert_close(g2.cpu().numpy(), r2, TOL, "corr gI2 %s %s" % (params, shape))
+
+
+def test_correlation_stride1_2_forward_only():
+    f = _f2()
+    a, b = _randn((1, 4, 12, 13), 1), _randn((1, 4, 12, 13), 2)
+    out = f.functional.correlation_forward(a.cuda(), b.cuda(), 2, 1, 4, 2, 2)
+    assert_close(out.cpu().numpy(), orc.correlation_forward(a.numpy(), b.numpy(), 2, 1, 4, 2, 2), TOL, "corr s1=2")
+    with pytest.raises(RuntimeError, match="stride1"):
+        f.functional.correlation_backward(a.cuda(), b.cuda(), out, 2, 1, 4, 2, 2)
+
+
+def test_correlation_known_answers_gpu():
+    f = _f2()
+    ones = torch.ones(1, 5, 8, 8, device="cuda")
+    out = f.Correlation(4, 1, 4, 1, 2, 1)(ones, ones)
+    assert out.shape == (1, 25, 8, 8)
+    assert torch.allclose(out[0, 12], torch.ones(8, 8, device="cuda"))
+    assert float(out[0, 0, 0, 0]) == 0.0 and abs(float(out[0, 0, 4, 4]) - 1.0) < 1e-6
+    f1 = _randn((1, 16, 16, 16), 3)
+    f2 = torch.roll(f1, (2, -4), dims=(2, 3))
+    out = f.Correlation(4, 1, 4, 1, 2, 1)(f1.cuda(), f2.cuda())
+    assert int(out[0, :, 8, 8].argmax()) == (1 + 2) * 5 + (-2 + 2)
+
+
+def test_correlation_autograd_module_and_noncontiguous():
+    """Module API + autograd plumbing; inputs/grad_output non-contiguous (the reference assumes
+    contiguity silently, SURVEY C-2; we accept a superset)."""
+    f = _f2()
+    base1 = _randn((2, 8, 12, 32), 5).cuda()
+    base2 = _randn((2, 8, 12, 32), 6).cuda()
+    a = base1.transpose(2, 3).contiguous().transpose(2, 3).requires_grad_()   # non-contiguous view
+    b = base2.clone().requires_grad_()
+    mod = f.Correlation(pad_size=20, kernel_size=1, max_displacement=20, stride1=1, stride2=2, corr_multiply=1)
+    out = mod(a, b)
+    go = _randn(tuple(out.shape), 7).cuda()
+    out.backward(go.transpose(2, 3).contiguous().transpose(2, 3))
+    r1, r2 = orc.correlation_backward(base1.cpu().numpy(), base2.cpu().numpy(), go.cpu().numpy(), 20, 1, 20, 1, 2)
+    assert_close(a.grad.cpu().numpy(), r1, TOL, "autograd gI1")
+    assert_close(b.grad.cpu().numpy(), r2, TOL, "autograd gI2")
+    # only one input requires grad -> the other gradient is skipped
+    a2 = base1.clone().requires_grad_()
+    f.Correlation(20, 1, 20, 1, 2, 1)(a2, base2).backward(go)
+    assert_close(a2.grad.cpu().numpy(), r1, TOL, "autograd gI1 only")
+
+
+def test_correlation_side_stream():
+    f = _f2()
+    a, b = _randn((1, 32, 16, 64), 8).cuda(), _randn((1, 32, 16, 64), 9).cuda()
+    ref = orc.correlation_forward(a.cpu().numpy(), b.cpu().numpy(), 20, 1, 20, 1, 2)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        out = f.functional.correlation_forward(a, b, 20, 1, 20, 1, 2)
+    s.synchronize()
+    assert_close(out.cpu().numpy(), ref, TOL, "corr on side stream")
+
+
+def test_correlation_full_size_cfg2_samples_and_linearity():
+    """BASELINE cfg2 [8,256,112,256]: two whole samples against the oracle + size-independent properties."""
+    f = _f2()
+    shape = (8, 256, 112, 256)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randn(*shape, device="cuda", generator=g)
+    b = torch.randn(*shape, device="cuda", generator=g)
+    out = f.functional.correlation_forward(a, b, 20, 1, 20, 1, 2)
+    assert out.shape == (8, 441, 112, 256) and bool(torch.isfinite(out).all())
+    for n in (0, 7):
+        ref = orc.correlation_forward(a[n:n + 1].cpu().numpy(), b[n:n + 1].cpu().numpy(), 20, 1, 20, 1, 2)
+        assert_close(out[n:n + 1].cpu().numpy(), ref, TOL, "cfg2 fwd sample %d" % n)
+    # linearity in input1 and symmetry under swapping inputs + negating displacements
+    out2 = f.functional.correlation_forward(a * 2.0, b, 20, 1, 20, 1, 2)
+    assert rel_err(out2.cpu().numpy(), (out * 2.0).cpu().numpy()) < 1e-6
+    del out2
+    sw = f.functional.correlation_forward(b[:1], a[:1], 20, 1, 20, 1, 2)          # out'(d, p) = out(-d, p + d)
+    d = 441 // 2 + 21 * 3 + 5                                                     # tj = 3, ti = 5
+    dneg = 441 // 2 - 21 * 3 - 5
+    lhs = sw[0, dneg, 6:100, 10:240]
+    rhs = out[0, d, 0:94, 0:230]
+    assert rel_err(lhs.cpu().numpy(), rhs.cpu().numpy()) < 1e-5
+    go = torch.randn(out.shape, device="cuda", generator=g)
+    g1, g2 = f.functional.correlation_backward(a, b, go, 20, 1, 20, 1, 2)
+    n = 3
+    r1, r2 = orc.correlation_backward(a[n:n + 1].cpu().numpy(), b[n:n + 1].cpu().numpy(), go[n:n + 1].cpu().numpy(),
+                                      20, 1, 20, 1, 2)
+    assert_close(g1[n:n + 1].cpu().numpy(), r1, TOL, "cfg2 gI1 sample %d" % n)
+    assert_close(g2[n:n + 1].cpu().numpy(), r2, TOL, "cfg2 gI2 sample %d" % n)
+    # adjoint identity: <corr(a,b), go> == <a, gI1> == <b, gI2>  (bilinear form)
+    s0 = float((out.double() * go.double()).sum())
+    s1 = float((a.double() * g1.double()).sum())
+    s2 = float((b.double() * g2.double()).sum())
+    assert abs(s0 - s1) <= 1e-4 * abs(s0) + 1e-3 and abs(s0 - s2) <= 1e-4 * abs(s0) + 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# Resample2d
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,sigma,C", [((2, 9, 13), 4.0, 3), ((1, 16, 20), 64.0, 3), ((2, 7, 5), 1.0, 2),
+                                           ((1, 8, 12), 3.0, 5), ((1, 12, 12), 0.0, 1)])
+def test_resample2d_vs_oracle(shape, sigma, C):
+    f = _f2()
+    B, H, W = shape
+    g = torch.Generator().manual_seed(21)
+    img = torch.rand(B, C, H, W, generator=g)
+    flow = torch.randn(B, 2, H, W, generator=g) * sigma
+    go = torch.randn(B, C, H, W, generator=g)
+    out = f.functional.resample2d_forward(img.cuda(), flow.cuda())
+    assert_close(out.cpu().numpy(), orc.resample2d_forward(img.numpy(), flow.numpy()), TOL, "resample fwd")
+    near = f.functional.resample2d_forward(img.cuda(), flow.cuda(), 1, False)
+    assert np.array_equal(near.cpu().numpy(), orc.resample2d_forward(img.numpy(), flow.numpy(), 1, False))
+    g1, g2 = f.functional.resample2d_backward(img.cuda(), flow.cuda(), go.cuda())
+    r1, r2 = orc.resample2d_backward(img.numpy(), flow.numpy(), go.numpy())
+    assert_close(g1.cpu().numpy(), r1, TOL, "resample gImg")
+    assert_close(g2.cpu().numpy(), r2, TOL, "resample gFlow")
+
+
+def test_resample2d_strided_image_slice_and_module():
+    """FlowNet2 passes x[:,3:,:,:] (non-contiguous, models.py:133); no .contiguous() copy needed."""
+    f = _f2()
+    g = torch.Generator().manual_seed(22)
+    x = torch.rand(2, 6, 16, 24, generator=g).cuda()
+    flow = (torch.randn(2, 2, 16, 24, generator=g) * 5).cuda().requires_grad_()
+    img = x[:, 3:, :, :].requires_grad_()
+    assert not img.is_contiguous()
+    out = f.Resample2d()(img, flow)
+    ref = orc.resample2d_forward(x[:, 3:].contiguous().cpu().numpy(), flow.detach().cpu().numpy())
+    assert_close(out.detach().cpu().numpy(), ref, TOL, "resample strided fwd")
+    go = torch.randn(out.shape, generator=g).cuda()
+    out.backward(go)
+    r1, r2 = orc.resample2d_backward(x[:, 3:].contiguous().cpu().numpy(), flow.detach().cpu().numpy(), go.cpu().numpy())
+    assert_close(img.grad.cpu().numpy(), r1, TOL, "resample strided gImg")
+    assert_close(flow.grad.cpu().numpy(), r2, TOL, "resample strided gFlow")
+    with pytest.raises(RuntimeError, match="kernel_size"):
+        f.Resample2d(kernel_size=2)(x[:, :3].contiguous(), flow.detach())
+
+
+def test_resample2d_full_size_properties():
+    """cfg3 shapes [8,3,448,1024]: identity under zero flow, shifted copy under integer flow,
+    and one sample against the oracle."""
+    f = _f2()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    img = torch.rand(8, 3, 448, 1024, device="cuda", generator=g)
+    zero = torch.zeros(8, 2, 448, 1024, device="cuda")
+    assert torch.equal(f.functional.resample2d_forward(img, zero), img)
+    sh = zero.clone()
+    sh[:, 0] = 3.0
+    sh[:, 1] = -2.0
+    out = f.functional.resample2d_forward(img, sh)
+    assert torch.equal(out[:, :, 2:, :-3], img[:, :, :-2, 3:])
+    flow = torch.randn(8, 2, 448, 1024, device="cuda", generator=g) * 4
+    out = f.functional.resample2d_forward(img, flow)
+    ref = orc.resample2d_forward(img[5:6].cpu().numpy(), flow[5:6].cpu().numpy())
+    assert_close(out[5:6].cpu().numpy(), ref, TOL, "cfg3 resample fwd sample 5")
+    go = torch.randn(8, 3, 448, 1024, device="cuda", generator=g)
+    g1, g2 = f.functional.resample2d_backward(img, flow, go)
+    r1, r2 = orc.resample2d_backward(img[5:6].cpu().numpy(), flow[5:6].cpu().numpy(), go[5:6].cpu().numpy())
+    assert_close(g1[5:6].cpu().numpy(), r1, TOL, "cfg3 resample gImg sample 5")
+    assert_close(g2[5:6].cpu().numpy(), r2, TOL, "cfg3 resample gFlow sample 5")
+    # mass conservation of the scatter: sum(gImg) == sum(go)  (bilinear weights sum to 1)
+    assert abs(float(g1.double().sum()) - float(go.double().sum())) < 1e-3 * float(go.double().abs().sum()) ** 0.5 + 1.0
+
+
+# ------------------------------------------------------------------------------------------------
+# ChannelNorm
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 3, 8, 12), (1, 2, 7, 9), (1, 1, 4, 4), (2, 5, 6, 10), (1, 7, 3, 3),
+                                   (8, 3, 448, 1024), (8, 2, 448, 1024)])
+def test_channelnorm_vs_oracle(shape):
+    f = _f2()
+    x = _randn(shape, 31)
+    x[0, :, 0, 0] = 0.0                                # exact-zero pixel: gradient must be 0 (N-1)
+    mod = f.ChannelNorm()
+    xc = x.cuda().requires_grad_()
+    out = mod(xc)
+    ref = orc.channelnorm_forward(x.numpy())
+    assert_close(out.detach().cpu().numpy(), ref, 1e-6, "cnorm fwd")
+    go = _randn(tuple(out.shape), 32)
+    out.backward(go.cuda())
+    assert_close(xc.grad.cpu().numpy(), orc.channelnorm_backward(x.numpy(), ref, go.numpy()), 1e-5, "cnorm bwd")
+    assert float(xc.grad[0, :, 0, 0].abs().max()) == 0.0
+
+
+def test_channelnorm_half_input_roundtrip():
+    """--fp16 mode feeds ChannelNorm half tensors (models.py:39 is not wrapped in tofp32)."""
+    f = _f2()
+    x = _randn((1, 3, 8, 8), 33).cuda().half()
+    out = f.ChannelNorm()(x)
+    assert out.dtype == torch.float16
+    assert torch.allclose(out.float(), x.float().pow(2).sum(1, keepdim=True).sqrt(), atol=2e-3, rtol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# Against the reference's own kernels (oracle/_ref) and through the reference's Python wrappers
+# ------------------------------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not oref.available(), reason="oracle/_ref reference extensions not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", [(1, 256, 48, 64), (2, 20, 13, 36)])
+def test_correlation_vs_reference_kernels(shape):
+    f = _f2()
+    refext = oref.load_extension("correlation_cuda")
+    a, b = _randn(shape, 41).cuda(), _randn(shape, 42).cuda()
+    r1, r2, rout = a.new_empty(0), a.new_empty(0), a.new_empty(0)
+    refext.forward(a, b, r1, r2, rout, 20, 1, 20, 1, 2, 1)
+    out = f.functional.correlation_forward(a, b, 20, 1, 20, 1, 2)
+    assert_close(out.cpu().numpy(), rout.cpu().numpy(), TOL, "ours vs reference kernel fwd")
+    assert_close(orc.correlation_forward(a.cpu().numpy(), b.cpu().numpy(), 20, 1, 20, 1, 2), rout.cpu().numpy(), 1e-5,
+                 "oracle vs reference kernel fwd")
+    go = _randn(tuple(rout.shape), 43).cuda()
+    gi1, gi2 = a.new_empty(0), a.new_empty(0)
+    refext.backward(a, b, a.new_empty(0), a.new_empty(0), go, gi1, gi2, 20, 1, 20, 1, 2, 1)
+    g1, g2 = f.functional.correlation_backward(a, b, go, 20, 1, 20, 1, 2)
+    assert_close(g1.cpu().numpy(), gi1.cpu().numpy(), TOL, "ours vs reference kernel gI1")
+    assert_close(g2.cpu().numpy(), gi2.cpu().numpy(), TOL, "ours vs reference kernel gI2")
+
+
+@needs_ref
+def test_resample_channelnorm_vs_reference_kernels():
+    f = _f2()
+    rs, cn = oref.load_extension("resample2d_cuda"), oref.load_extension("channelnorm_cuda")
+    g = torch.Generator().manual_seed(44)
+    img = torch.rand(2, 3, 32, 48, generator=g).cuda()
+    flow = (torch.randn(2, 2, 32, 48, generator=g) * 6).cuda()
+    go = torch.randn(2, 3, 32, 48, generator=g).cuda()
+    rout = torch.zeros_like(img)
+    rs.forward(img, flow, rout, 1, True)
+    assert_close(f.functional.resample2d_forward(img, flow).cpu().numpy(), rout.cpu().numpy(), TOL, "resample fwd vs ref")
+    rg1, rg2 = torch.zeros_like(img), torch.zeros_like(flow)
+    rs.backward(img, flow, go, rg1, rg2, 1, True)
+    g1, g2 = f.functional.resample2d_backward(img, flow, go)
+    assert_close(g1.cpu().numpy(), rg1.cpu().numpy(), TOL, "resample gImg vs ref")
+    assert_close(g2.cpu().numpy(), rg2.cpu().numpy(), TOL, "resample gFlow vs ref")
+    x = torch.randn(2, 3, 32, 48, generator=g).cuda()
+    ro = torch.zeros(2, 1, 32, 48, device="cuda")
+    cn.forward(x, ro, 2)
+    o = f.functional.channelnorm_forward(x)
+    assert_close(o.cpu().numpy(), ro.cpu().numpy(), 1e-6, "cnorm fwd vs ref")
+    gon = torch.randn(2, 1, 32, 48, generator=g).cuda()
+    rgi = torch.zeros_like(x)
+    cn.backward(x, ro, gon, rgi, 2)
+    assert_close(f.functional.channelnorm_backward(x, o, gon).cpu().numpy(), rgi.cpu().numpy(), 1e-5, "cnorm bwd vs ref")
+
+
+needs_models = pytest.mark.skipif(not (oref.available() and oref.python_tree_available()),
+                                  reason="reference python tree / extensions not installed under baseline/_ref, oracle/_ref")
+
+
+def _build_ref_model(name, level):
+    """Instantiate the UNMODIFIED reference models.<name> on top of (a) the reference kernels,
+    (b) our B1 extension shims, (c) our B2 layer modules."""
+    import sys
+    from types import SimpleNamespace
+    from flownet2_b200 import compat
+    compat.uninstall()
+    if level == "ref":
+        oref.install_reference_extensions()
+    else:
+        compat.install(level)
+    models = oref.import_reference_models(fresh=True)
+    torch.manual_seed(0)
+    net = getattr(models, name)(SimpleNamespace(rgb_max=255.0, fp16=False)).cuda().eval()
+    return net
+
+
+@needs_models
+@pytest.mark.parametrize("name", ["FlowNet2C", "FlowNet2"])
+def test_unmodified_reference_models_run_on_our_layers(name):
+    """models.py's stacks load our layers unchanged (B1 and B2) and agree with the
+    reference kernels on identical weights/inputs."""
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(1, 3, 2, 128, 192, generator=g) * 255.0).cuda()
+    outs = {}
+    for level in ("ref", "B1", "B2"):
+        net = _build_ref_model(name, level)
+        with torch.no_grad():
+            outs[level] = net(x).float().cpu().numpy()
+        kinds = {type(m).__module__ for m in net.modules() if type(m).__name__ in ("Correlation", "Resample2d", "ChannelNorm")}
+        if level == "B2":
+            assert all(k.startswith("flownet2_b200") for k in kinds), kinds
+        else:
+            assert all(k.startswith("networks.") for k in kinds), kinds
+        del net
+    from flownet2_b200 import compat
+    compat.uninstall()
+    assert np.isfinite(outs["ref"]).all()
+    assert rel_err(outs["B1"], outs["ref"]) < 1e-3, rel_err(outs["B1"], outs["ref"])
+    assert rel_err(outs["B2"], outs["ref"]) < 1e-3, rel_err(outs["B2"], outs["ref"])
