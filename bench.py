@@ -54,47 +54,79 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (NVML in a thread, 5 ms period;
+    falls back to the nvidia-smi loop of B200_PROFILING.md when pynvml is unusable)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+    def __init__(self, cuda_index):
+        self.idx, self.rows, self._stop, self.h, self.proc, self.t = cuda_index, [], False, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(self.idx).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+        except Exception:
+            self.h = None
+            self._start_smi()
+
+    def _nvml_loop(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.time(), sm, self.max_mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t = threading.Thread(target=self._smi_loop, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _pump(self):
+    def _smi_loop(self):
+        bits = [0x8, 0x40, 0x20, 0x4]
         for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
-
-    def window(self, t0, t1):
-        rows = [l for (t, l) in self.lines if t0 <= t <= t1] or [l for (_, l) in self.lines[-3:]]
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
+            f = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                for nm, v in zip(names, f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                mask = sum(b for b, v in zip(bits, f[2:6]) if v.lower().startswith("active"))
+                self.rows.append((time.time(), float(f[0]), float(f[1]), mask))
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def window(self, t0, t1):
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        sm = sorted(r[1] for r in rows)
+        mask = 0
+        for r in rows:
+            mask |= r[3]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(r[2] for r in rows) if rows else None,
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(sm)}
 
     def stop(self):
+        self._stop = True
         if self.proc:
             self.proc.terminate()
 

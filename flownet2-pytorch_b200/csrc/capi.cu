@@ -32,6 +32,25 @@ int check_launch(const char *what) {
     return 0;
 }
 
+// Bind the calling thread to the device that owns `ptr`.  Worker threads (the autograd engine,
+// nn.DataParallel replicas) may have no CUDA context current yet -- torch's device guard skips
+// cudaSetDevice when the index already matches -- and driver calls such as
+// cuTensorMapEncodeTiled then fail with CUDA_ERROR_INVALID_CONTEXT.
+int bind_device_of(const void *ptr) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail((int)e, "cudaPointerGetAttributes failed (%s)", cudaGetErrorString(e));
+    }
+    if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)
+        return fail(FN2B200_EINVAL, "pointer %p is not device memory (type %d): the C ABI takes device "
+                    "pointers only", ptr, (int)a.type);
+    e = cudaSetDevice(a.device);
+    if (e != cudaSuccess) return fail((int)e, "cudaSetDevice(%d) failed (%s)", a.device, cudaGetErrorString(e));
+    return 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -130,6 +149,7 @@ int fn2b200_correlation_forward(const float *in1, const float *in2, float *out, 
     if (rc) return rc;
     if (B == 0) return 0;
     if (!in1 || !in2 || !out) return fail(FN2B200_ENULL, "correlation_forward: null pointer");
+    if ((rc = bind_device_of(in1))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (corr_tiled_supported(p)) return corr_forward_tiled(in1, in2, out, p, st);
     return corr_forward_generic(in1, in2, out, p, st);
@@ -150,6 +170,7 @@ int fn2b200_correlation_backward(const float *in1, const float *in2, const float
     if (B == 0) return 0;
     if (!in1 || !in2 || !gout) return fail(FN2B200_ENULL, "correlation_backward: null pointer");
     if (!gin1 && !gin2) return 0;
+    if ((rc = bind_device_of(in1))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (corr_tiled_supported(p)) return corr_backward_tiled(in1, in2, gout, gin1, gin2, p, st);
     return corr_backward_generic(in1, in2, gout, gin1, gin2, p, st);
@@ -181,6 +202,7 @@ int fn2b200_resample2d_forward(const float *img, const int64_t *istride, const f
     if (rc) return rc;
     if (B == 0) return 0;
     if (!img || !flow || !out) return fail(FN2B200_ENULL, "resample2d_forward: null pointer");
+    if ((rc = bind_device_of(flow))) return rc;
     return resample2d_forward(img, istride, flow, out, B, C, iH, iW, H, W, bilinear,
                               (cudaStream_t)stream);
 }
@@ -194,6 +216,7 @@ int fn2b200_resample2d_backward(const float *img, const int64_t *istride, const 
     if (rc) return rc;
     if (B == 0) return 0;
     if (!img || !flow || !gout) return fail(FN2B200_ENULL, "resample2d_backward: null pointer");
+    if ((rc = bind_device_of(flow))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (gimg && zero_grad_input1) {
         cudaError_t e = cudaMemsetAsync(gimg, 0, sizeof(float) * (size_t)B * C * iH * iW, st);
@@ -213,6 +236,7 @@ int fn2b200_channelnorm_forward(const float *in, float *out, int B, int C, int H
         return fail(FN2B200_EINVAL, "channelnorm_forward: tensor exceeds 2^31 elements");
     if (B == 0) return 0;
     if (!in || !out) return fail(FN2B200_ENULL, "channelnorm_forward: null pointer");
+    if (int rc = bind_device_of(in)) return rc;
     return channelnorm_forward(in, out, B, C, H, W, (cudaStream_t)stream);
 }
 
@@ -226,6 +250,7 @@ int fn2b200_channelnorm_backward(const float *in, const float *out, const float 
     if (B == 0) return 0;
     if (!in || !out || !gout || !gin)
         return fail(FN2B200_ENULL, "channelnorm_backward: null pointer");
+    if (int rc = bind_device_of(in)) return rc;
     return channelnorm_backward(in, out, gout, gin, B, C, H, W, (cudaStream_t)stream);
 }
 

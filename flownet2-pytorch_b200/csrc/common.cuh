@@ -17,7 +17,8 @@ namespace fn2 {
 void set_error(const char *fmt, ...);
 int fail(int code, const char *fmt, ...);
 void count_launch(int n = 1);
-int check_launch(const char *what);  // cudaGetLastError -> return code (+ message)
+int check_launch(const char *what);
+int bind_device_of(const void *ptr);  // make the device owning ptr current on this thread  // cudaGetLastError -> return code (+ message)
 
 // ---- TMA descriptor creation (driver entry point resolved through the runtime; no -lcuda) --
 // Encodes a tiled tensor map over an fp32 tensor of `rank` dims (dims[0] fastest).

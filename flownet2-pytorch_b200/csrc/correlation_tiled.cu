@@ -333,12 +333,15 @@ corr_bwd_tiled_kernel(const __grid_constant__ CUtensorMap map_other,
 // ------------------------------------------------------------------------------------------------
 static inline bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
-#define FN2_TILED_CONFIGS(X) X(2, 10) X(2, 4) X(1, 4) X(1, 3) X(2, 2)
+// (stride2, displacement radius) pairs with a compiled tiled kernel; the x halo dr*s2 must be a
+// multiple of 4 (TMA traps on a dim-0 start coordinate that is not 16-byte aligned -- measured).
+#define FN2_TILED_CONFIGS(X) X(2, 10) X(2, 4) X(1, 4) X(2, 2)
 
 bool corr_tiled_supported(const CorrParams &p) {
     if (p.k != 1 || p.s1 != 1) return false;
     if (p.W % 4 != 0) return false;  // TMA global strides must be multiples of 16 bytes
     if (p.oW % 4 != 0) return false;  // gradOutput is a TMA source in backward
+    if ((p.md - p.pad) % 4 != 0) return false;  // box x start = tile + (md - pad): must stay 16-B aligned
 #define X(S2_, DR_) if (p.s2 == S2_ && p.dr == DR_) return true;
     FN2_TILED_CONFIGS(X)
 #undef X

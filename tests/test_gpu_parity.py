@@ -35,12 +35,13 @@ CORR_CASES = [
     ((20, 1, 20, 1, 2), (2, 20, 13, 192), 1),     # odd H, C % 8 != 0, 1.5 tiles wide
     ((20, 1, 20, 1, 2), (1, 3, 5, 8), 1),         # tiny: W < tile, H < row quad
     ((20, 1, 20, 1, 2), (1, 64, 9, 260), 1),      # 3 tiles wide, ragged last tile
-    ((22, 1, 20, 1, 2), (1, 16, 10, 32), 1),      # pad > md (output larger than input), tiled
-    ((18, 1, 20, 1, 2), (1, 16, 14, 32), 1),      # pad < md (output smaller), tiled
+    ((24, 1, 20, 1, 2), (1, 16, 10, 32), 1),      # pad > md (output larger than input), tiled
+    ((16, 1, 20, 1, 2), (1, 16, 14, 32), 1),      # pad < md (output smaller), tiled
+    ((22, 1, 20, 1, 2), (1, 16, 10, 32), 0),      # (md - pad) % 4 != 0 -> generic (TMA start alignment)
     ((4, 1, 4, 1, 2), (2, 7, 9, 12), 1),          # (s2, dr) = (2, 2)
     ((8, 1, 8, 1, 2), (1, 9, 11, 16), 1),         # (2, 4)
     ((4, 1, 4, 1, 1), (1, 5, 8, 16), 1),          # (1, 4)
-    ((3, 1, 3, 1, 1), (1, 5, 8, 8), 1),           # (1, 3): odd halo
+    ((3, 1, 3, 1, 1), (1, 5, 8, 8), 0),           # (1, 3): odd halo -> generic
     ((5, 1, 5, 1, 2), (1, 6, 8, 8), 1),           # md % s2 != 0 -> dr = 2
     ((4, 3, 4, 1, 2), (1, 6, 10, 12), 0),         # kernel_size 3 -> generic
     ((4, 1, 4, 1, 2), (1, 6, 9, 11), 0),          # W % 4 != 0 -> generic
