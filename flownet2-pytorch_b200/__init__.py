@@ -12,7 +12,7 @@ plus ``functional`` (tensor-level calls into the C ABI) and ``compat`` (hooks fo
 unmodified reference models.py).  The CUDA library is mandatory: importing this package without
 ``libfn2b200.so`` raises, and CPU tensors are rejected -- there is no fallback path.
 """
-from . import _lib, compat, functional  # noqa: F401
+from . import _lib, compat, functional, sharding  # noqa: F401
 from .channelnorm import ChannelNorm, ChannelNormFunction  # noqa: F401
 from .correlation import Correlation, CorrelationFunction  # noqa: F401
 from .resample2d import Resample2d, Resample2dFunction  # noqa: F401

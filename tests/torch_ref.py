@@ -19,11 +19,14 @@ def correlation(f1, f2, pad_size, kernel_size, max_displacement, stride1, stride
     dr = max_displacement // stride2
     oH = int(math.ceil((pH - 2 * br) / stride1))
     oW = int(math.ceil((pW - 2 * br) / stride1))
-    p1 = F.pad(f1, (pad_size,) * 4)
-    p2 = F.pad(f2, (pad_size,) * 4)
+    # extra zero margin so the kernel_size > 1 border taps (row/col -1 and pH/pW of the padded buffer,
+    # which the reference reads out of bounds) are explicit zeros instead of wrapped indices
+    ex = kr + 1
+    p1 = F.pad(f1, (pad_size + ex,) * 4)
+    p2 = F.pad(f2, (pad_size + ex,) * 4)
     outs = []
-    ys = torch.arange(oH, device=f1.device) * stride1 + max_displacement
-    xs = torch.arange(oW, device=f1.device) * stride1 + max_displacement
+    ys = torch.arange(oH, device=f1.device) * stride1 + max_displacement + ex
+    xs = torch.arange(oW, device=f1.device) * stride1 + max_displacement + ex
     for tj in range(-dr, dr + 1):
         for ti in range(-dr, dr + 1):
             acc = 0
