@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace fn2 {
 
@@ -84,6 +85,34 @@ int make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, const uint
     return 0;
 }
 
+int make_tensor_map_bf16_sw128(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
+                               const uint64_t *strides_bytes, const uint32_t *box) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess)
+        return fail(e != cudaSuccess ? (int)e : (int)cudaErrorNotSupported,
+                    "cuTensorMapEncodeTiled entry point unavailable (err %d)", (int)e);
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i + 1 < rank) gstr[i] = strides_bytes[i];
+    }
+    CUresult r = ((EncodeTiledFn)fn)(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                                     const_cast<void *>(base), gdim, gstr, bdim, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail((int)cudaErrorInvalidValue, "cuTensorMapEncodeTiled(bf16, SW128) failed (CUresult %d)", (int)r);
+    return 0;
+}
+
+int umma_selftest(const void *A, const void *B, float *D, int K, cudaStream_t st);
+
 static int fill_corr_params(CorrParams &p, int B, int C, int H, int W, int pad, int k, int md,
                             int s1, int s2) {
     if (B < 0 || C <= 0 || H <= 0 || W <= 0)
@@ -117,6 +146,12 @@ using namespace fn2;
 extern "C" {
 
 int fn2b200_version(void) { return FN2B200_VERSION; }
+
+int fn2b200_debug_umma_gemm(const void *A_bf16, const void *B_bf16, float *D, int K, void *stream) {
+    if (!A_bf16 || !B_bf16 || !D) return fail(FN2B200_ENULL, "debug_umma_gemm: null pointer");
+    if (int rc = bind_device_of(D)) return rc;
+    return umma_selftest(A_bf16, B_bf16, D, K, (cudaStream_t)stream);
+}
 const char *fn2b200_last_error(void) { return g_err; }
 uint64_t fn2b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -1,0 +1,84 @@
+// umma_selftest.cu -- hardware self-test of the tcgen05 / TMEM / TMA-swizzle plumbing in umma.cuh.
+// D[128 x N] (fp32) = A[128 x K] * B[N x K]^T with bf16 operands, K a multiple of 64, N = 144.
+// Exposed as fn2b200_debug_umma_gemm (tests/test_gpu_umma.py compares with a CPU product).
+#include "umma.cuh"
+
+namespace fn2 {
+
+constexpr int ST_M = 128, ST_N = 144, ST_KB = 64;
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     float *__restrict__ D, int K) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sA = smem;                         // [128 rows][128 B], SW128
+    unsigned char *sB = smem + ST_M * 128;            // [144 rows][128 B], SW128
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + ST_N * 128);   // [0] full, [1] mma done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = umma_idesc_bf16_f32(ST_M, ST_N);
+
+    const int nkb = K / ST_KB;
+    for (int kb = 0; kb < nkb; ++kb) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bars[0], (ST_M + ST_N) * 128);
+            tma_load_2d(sA, &mapA, &bars[0], kb * ST_KB, 0);
+            tma_load_2d(sB, &mapB, &bars[0], kb * ST_KB, 0);
+            mbar_wait(&bars[0], kb & 1);
+            tcgen05_fence_after();
+            const uint64_t da = umma_desc_k_sw128(smem_u32(sA));
+            const uint64_t db = umma_desc_k_sw128(smem_u32(sB));
+#pragma unroll
+            for (int ks = 0; ks < ST_KB / 16; ++ks)   // advance 16 bf16 = 32 B = 2 x 16-byte units
+                umma_bf16_ss(tmem_base, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0);
+            umma_commit(&bars[1]);
+            mbar_wait(&bars[1], kb & 1);              // smem may be overwritten by the next block
+        }
+        __syncthreads();
+    }
+    tcgen05_fence_after();
+    // epilogue: warp w reads TMEM lanes [32w, 32w+32), all 144 columns
+    const int row = tid;
+    for (int c0 = 0; c0 < ST_N; c0 += 16) {
+        float r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) D[row * ST_N + c0 + j] = r[j];
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
+int umma_selftest(const void *A, const void *B, float *D, int K, cudaStream_t st) {
+    if (K <= 0 || K % ST_KB) return fail(FN2B200_EINVAL, "umma_selftest: K must be a positive multiple of 64");
+    CUtensorMap ma, mb;
+    uint64_t dimsA[2] = {(uint64_t)K, ST_M}, dimsB[2] = {(uint64_t)K, ST_N};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t boxA[2] = {ST_KB, ST_M}, boxB[2] = {ST_KB, ST_N};
+    int rc = make_tensor_map_bf16_sw128(&ma, A, 2, dimsA, str, boxA);
+    if (rc) return rc;
+    rc = make_tensor_map_bf16_sw128(&mb, B, 2, dimsB, str, boxB);
+    if (rc) return rc;
+    const int smem = (ST_M + ST_N) * 128 + 1024 + 64;
+    cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail((int)e, "umma_selftest: smem attribute (%s)", cudaGetErrorString(e));
+    umma_selftest_kernel<<<1, 128, smem, st>>>(ma, mb, D, K);
+    count_launch();
+    return check_launch("umma_selftest");
+}
+
+}  // namespace fn2

@@ -117,6 +117,13 @@ int fn2b200_channelnorm_backward(const float *input1, const float *output,
 int fn2b200_correlation_path(int C, int H, int W, int pad_size, int kernel_size,
                              int max_displacement, int stride1, int stride2);
 
+/*
+ * Hardware self-test of the tcgen05 / TMEM / TMA-swizzle plumbing the tensor-core correlation path
+ * is built on: D[128 x 144] (fp32, row-major) = A[128 x K] * B[144 x K]^T, A and B bf16 row-major
+ * device buffers, K a multiple of 64.  Test hook only (tests/test_gpu_umma.py).
+ */
+int fn2b200_debug_umma_gemm(const void *A_bf16, const void *B_bf16, float *D, int K, void *stream);
+
 /* Number of kernel launches (ours) issued by this library in this process so far (statistics). */
 uint64_t fn2b200_launch_count(void);
 
