@@ -2,6 +2,7 @@
 #include <math.h>
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -139,6 +140,13 @@ static int fill_corr_params(CorrParams &p, int B, int C, int H, int W, int pad, 
     return 0;
 }
 
+// FN2B200_CORR_FWD = "fma" forces the FP32-FMA kernels, "tc" (default) uses tensor cores when the
+// configuration supports them and a workspace is supplied.  Read per call: no cached state.
+static bool tc_enabled() {
+    const char *e = getenv("FN2B200_CORR_FWD");
+    return !(e && (e[0] == 'f' || e[0] == 'F'));
+}
+
 }  // namespace fn2
 
 using namespace fn2;
@@ -172,6 +180,7 @@ int fn2b200_correlation_out_shape(int C, int H, int W, int pad, int k, int md, i
 int fn2b200_correlation_path(int C, int H, int W, int pad, int k, int md, int s1, int s2) {
     CorrParams p;
     if (fill_corr_params(p, 1, C, H, W, pad, k, md, s1, s2)) return -1;
+    if (tc_enabled() && corr_tc_supported(p)) return 2;
     return corr_tiled_supported(p) ? 1 : 0;
 }
 
@@ -188,6 +197,29 @@ int fn2b200_correlation_forward(const float *in1, const float *in2, float *out, 
     cudaStream_t st = (cudaStream_t)stream;
     if (corr_tiled_supported(p)) return corr_forward_tiled(in1, in2, out, p, st);
     return corr_forward_generic(in1, in2, out, p, st);
+}
+
+size_t fn2b200_correlation_forward_workspace(int B, int C, int H, int W, int pad, int k, int md, int s1,
+                                             int s2) {
+    CorrParams p;
+    if (fill_corr_params(p, B, C, H, W, pad, k, md, s1, s2)) return 0;
+    if (!tc_enabled()) return 0;
+    return corr_tc_workspace_bytes(p);
+}
+
+int fn2b200_correlation_forward_ws(const float *in1, const float *in2, float *out, int B, int C, int H,
+                                   int W, int pad, int k, int md, int s1, int s2, int corr_type_multiply,
+                                   void *workspace, size_t workspace_bytes, void *stream) {
+    CorrParams p;
+    int rc = fill_corr_params(p, B, C, H, W, pad, k, md, s1, s2);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!in1 || !in2 || !out) return fail(FN2B200_ENULL, "correlation_forward: null pointer");
+    if (workspace && tc_enabled() && corr_tc_supported(p) && workspace_bytes >= corr_tc_workspace_bytes(p)) {
+        if ((rc = bind_device_of(in1))) return rc;
+        return corr_forward_tc(in1, in2, out, p, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
+    return fn2b200_correlation_forward(in1, in2, out, B, C, H, W, pad, k, md, s1, s2, corr_type_multiply, stream);
 }
 
 int fn2b200_correlation_backward(const float *in1, const float *in2, const float *gout,

@@ -1,0 +1,305 @@
+// correlation_tc.cu -- tensor-core (tcgen05 / TMEM) correlation FORWARD for FlowNetC's configuration
+// (kernel_size 1, stride1 1, stride2 2, displacement radius 10, pad == max_displacement).
+//
+// Formulation.  stride2 = 2 means output pixel (y,x) only meets f2 pixels of
+// the same (y mod 2, x mod 2) parity class, so each of the 4 classes is a stride-1 correlation on a
+// half-resolution grid (Hc x Wc) with displacements tj,ti in [-10,10].  For a tile of 8 x 16 class
+// pixels (M = 128 rows) the needed f2 pixels are the 28 x 36 halo; the cost volume is the band
+// |tj|,|ti| <= 10 of the dense product
+//        S[p, q] = sum_c f1[c, p] * f2[c, q]        (p in tile, q in halo),
+// computed as a GEMM in 7 "units" of 4 halo rows (N = 144 columns) over K = C channels.
+// fp32 accuracy on bf16 tensor cores: every operand is split x = hi + lo (two bf16, 16 significand
+// bits); S = hi*hi + hi*lo + lo*hi (3 MMAs, fp32 accumulate in TMEM), dropped lo*lo ~ 2^-18 relative.
+//
+// Pipeline (one persistent CTA per SM, warp-specialised, 192 threads):
+//   prepass kernel : NCHW fp32 -> [n][class][yc][xc][c] bf16 hi / lo (channels contiguous = K-major)
+//   warp 0 (TMA)   : f1 tile  -> smem A [hi|lo][C/64][128 rows x 128 B]  (resident for the 7 units)
+//                    f2 units -> smem B ring [2 stages][hi|lo][144 rows x 128 B], 128-byte swizzle;
+//                    halo outside the image = TMA out-of-bounds zero fill = the layer's zero padding
+//   warp 1 (MMA)   : tcgen05.mma.kind::f16 M128 N144 K16, 3 products x 4 k-steps per 64-channel
+//                    stage, accumulators in TMEM (3 buffers x 144 columns), tcgen05.commit -> mbarriers
+//   warps 2-5      : tcgen05.ld the accumulator rows (lane = tile pixel), pick the 21 band entries of
+//                    each halo row through a per-thread shared-memory row (dynamic column offset),
+//                    scale by 1/C and store to out[n][(tj,ti)][y][x]
+#include "umma.cuh"
+#include <cuda_bf16.h>
+
+namespace fn2 {
+
+constexpr int TC_TH = 8, TC_TW = 16, TC_DR = 10;
+constexpr int TC_HH = TC_TH + 2 * TC_DR;      // 28 halo rows
+constexpr int TC_HW = TC_TW + 2 * TC_DR;      // 36 halo cols
+constexpr int TC_UR = 4;                       // halo rows per unit
+constexpr int TC_NU = TC_HH / TC_UR;           // 7 units per tile
+constexpr int TC_N = TC_UR * TC_HW;            // 144 accumulator columns per unit
+constexpr int TC_KB = 64;                      // channels per k-block (128 B of bf16)
+constexpr int TC_MAXKB = 4;                    // C <= 256
+constexpr int TC_BST = 2;                      // B ring stages
+constexpr int TC_NACC = 3;                     // TMEM accumulator buffers
+constexpr int TC_DS = 2 * TC_DR + 1;           // 21
+constexpr int TC_ABLK = 128 * 128;             // bytes of one A k-block (128 rows x 128 B)
+constexpr int TC_BBLK = TC_N * 128;            // bytes of one B k-block (144 rows x 128 B)
+constexpr int TC_EPITCH = TC_HW + 1;           // 37 floats per epilogue staging row
+constexpr int TC_SMEM_A = 2 * TC_MAXKB * TC_ABLK;          // 131072
+constexpr int TC_SMEM_B = TC_BST * 2 * TC_BBLK;            // 73728
+constexpr int TC_SMEM_E = 128 * TC_EPITCH * 4;             // 18944
+constexpr int TC_NBAR = 2 * TC_MAXKB + 2 * TC_BST + 2 * TC_NACC;
+constexpr int TC_SMEM = TC_SMEM_A + TC_SMEM_B + TC_SMEM_E + TC_NBAR * 8 + 16 + 1024;
+
+// ------------------------------------------------------------------------------------------------
+// Prepass: NCHW fp32 -> parity-class-separated NHWC bf16 hi / lo
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+corr_tc_split_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ hi,
+                     __nv_bfloat16 *__restrict__ lo, int C, int H, int W) {
+    __shared__ float tile[64][65];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int n = blockIdx.z / H, y = blockIdx.z % H;
+    const int Hc = H >> 1, Wc = W >> 1;
+    {
+        const int xo = tid & 63, cs = tid >> 6;
+        const float *src = in + (((long)n * C + c0) * H + y) * W + x0 + xo;
+        const bool ok = x0 + xo < W;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int c = i * 4 + cs;
+            tile[c][xo] = ok ? ldg_stream1(src + (long)c * H * W) : 0.f;
+        }
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int xo = warp * 8 + j, x = x0 + xo;
+        if (x >= W) break;
+        const int cls = (y & 1) * 2 + (x & 1);
+        const long row = (((long)(n * 4 + cls) * Hc + (y >> 1)) * Wc + (x >> 1)) * C + c0 + 2 * lane;
+        const float v0 = tile[2 * lane][xo], v1 = tile[2 * lane + 1][xo];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+        *reinterpret_cast<__nv_bfloat162 *>(hi + row) = __halves2bfloat162(h0, h1);
+        *reinterpret_cast<__nv_bfloat162 *>(lo + row) = __halves2bfloat162(l0, l1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Main kernel
+// ------------------------------------------------------------------------------------------------
+struct TcTile {
+    int n, py, px, yc0, xc0;
+};
+__device__ __forceinline__ TcTile tc_decode(int t, int nxt, int nyt) {
+    TcTile r;
+    r.px = t & 1;
+    int q = t >> 1;
+    r.xc0 = (q % nxt) * TC_TW;
+    q /= nxt;
+    r.yc0 = (q % nyt) * TC_TH;
+    q /= nyt;
+    r.py = q & 1;
+    r.n = q >> 1;
+    return r;
+}
+
+__global__ void __launch_bounds__(192, 1)
+corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ CUtensorMap m1l,
+                   const __grid_constant__ CUtensorMap m2h, const __grid_constant__ CUtensorMap m2l,
+                   float *__restrict__ out, int B, int C, int H, int W, int ntiles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sA = smem;                                   // [hl][kb][128 x 128 B]
+    unsigned char *sB = smem + TC_SMEM_A;                       // [stage][hl][144 x 128 B]
+    float *sE = reinterpret_cast<float *>(sB + TC_SMEM_B);      // [128][37]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(sE) + TC_SMEM_E);
+    uint64_t *a_full = bars, *a_empty = bars + TC_MAXKB;
+    uint64_t *b_full = bars + 2 * TC_MAXKB, *b_empty = b_full + TC_BST;
+    uint64_t *acc_full = b_empty + TC_BST, *acc_empty = acc_full + TC_NACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + TC_NBAR);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Hc = H >> 1, Wc = W >> 1;
+    const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
+    const int nkb = C / TC_KB;
+
+    if (tid == 0) {
+        prefetch_tensormap(&m1h); prefetch_tensormap(&m1l);
+        prefetch_tensormap(&m2h); prefetch_tensormap(&m2l);
+        for (int i = 0; i < TC_MAXKB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < TC_BST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t bcount = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const TcTile T = tc_decode(t, nxt, nyt);
+                const int img = T.n * 4 + T.py * 2 + T.px;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&a_empty[kb], (it & 1) ^ 1);
+                    mbar_arrive_expect_tx(&a_full[kb], 2 * TC_ABLK);
+                    tma_load_4d(sA + (0 * TC_MAXKB + kb) * TC_ABLK, &m1h, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
+                    tma_load_4d(sA + (1 * TC_MAXKB + kb) * TC_ABLK, &m1l, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
+                }
+                for (int u = 0; u < TC_NU; ++u)
+                    for (int kb = 0; kb < nkb; ++kb, ++bcount) {
+                        const int s = bcount % TC_BST;
+                        mbar_wait(&b_empty[s], ((bcount / TC_BST) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&b_full[s], 2 * TC_BBLK);
+                        tma_load_4d(sB + (s * 2 + 0) * TC_BBLK, &m2h, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
+                                    T.yc0 - TC_DR + u * TC_UR, img);
+                        tma_load_4d(sB + (s * 2 + 1) * TC_BBLK, &m2l, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
+                                    T.yc0 - TC_DR + u * TC_UR, img);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_f32(128, TC_N);
+            uint32_t bcount = 0, acount = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                for (int u = 0; u < TC_NU; ++u, ++acount) {
+                    const int ab = acount % TC_NACC;
+                    mbar_wait(&acc_empty[ab], ((acount / TC_NACC) & 1) ^ 1);
+                    tcgen05_fence_after();
+                    const uint32_t d = tmem_base + ab * TC_N;
+                    for (int kb = 0; kb < nkb; ++kb, ++bcount) {
+                        if (u == 0) mbar_wait(&a_full[kb], it & 1);
+                        const int s = bcount % TC_BST;
+                        mbar_wait(&b_full[s], (bcount / TC_BST) & 1);
+                        tcgen05_fence_after();
+                        const uint64_t ah = umma_desc_k_sw128(smem_u32(sA + (0 * TC_MAXKB + kb) * TC_ABLK));
+                        const uint64_t al = umma_desc_k_sw128(smem_u32(sA + (1 * TC_MAXKB + kb) * TC_ABLK));
+                        const uint64_t bh = umma_desc_k_sw128(smem_u32(sB + (s * 2 + 0) * TC_BBLK));
+                        const uint64_t bl = umma_desc_k_sw128(smem_u32(sB + (s * 2 + 1) * TC_BBLK));
+#pragma unroll
+                        for (int ks = 0; ks < TC_KB / 16; ++ks) {
+                            umma_bf16_ss(d, ah + 2 * ks, bh + 2 * ks, idesc, (kb | ks) != 0);
+                            umma_bf16_ss(d, ah + 2 * ks, bl + 2 * ks, idesc, 1);
+                            umma_bf16_ss(d, al + 2 * ks, bh + 2 * ks, idesc, 1);
+                        }
+                        umma_commit(&b_empty[s]);                    // stage may be refilled
+                        if (u == TC_NU - 1) umma_commit(&a_empty[kb]);  // A block free for the next tile
+                    }
+                    umma_commit(&acc_full[ab]);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int p = quad * 32 + lane;            // tile pixel = TMEM lane = accumulator row
+        const int py_t = p >> 4, px_t = p & 15;
+        float *row = sE + p * TC_EPITCH;
+        const float nelems = (float)C;
+        const long plane = (long)H * W;
+        uint32_t acount = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const TcTile T = tc_decode(t, nxt, nyt);
+            const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
+            const bool pix_ok = (yc < Hc) && (xc < Wc);
+            float *obase = out + (long)T.n * (TC_DS * TC_DS) * plane + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
+            for (int u = 0; u < TC_NU; ++u, ++acount) {
+                const int ab = acount % TC_NACC;
+                mbar_wait(&acc_full[ab], (acount / TC_NACC) & 1);
+                tcgen05_fence_after();
+#pragma unroll 1
+                for (int hrl = 0; hrl < TC_UR; ++hrl) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ab * TC_N + hrl * TC_HW;
+                    float r[TC_HW];
+                    tmem_ld16(taddr, r);
+                    tmem_ld16(taddr + 16, r + 16);
+                    tmem_ld4(taddr + 32, r + 32);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < TC_HW; ++j) row[j] = r[j];
+                    const int tj = u * TC_UR + hrl - py_t;          // = tj + DR, valid in [0, 20]
+                    if (pix_ok && tj >= 0 && tj < TC_DS) {
+                        float *o = obase + (long)(tj * TC_DS) * plane;
+                        const float *rp = row + px_t;
+#pragma unroll
+                        for (int ti = 0; ti < TC_DS; ++ti) o[ti * plane] = rp[ti] / nelems;
+                    }
+                }
+                tcgen05_fence_before();
+                mbar_arrive(&acc_empty[ab]);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+bool corr_tc_supported(const CorrParams &p) {
+    return p.k == 1 && p.s1 == 1 && p.s2 == 2 && p.dr == TC_DR && p.pad == p.md && (p.H % 2 == 0) &&
+           (p.W % 2 == 0) && (p.C % TC_KB == 0) && p.C <= TC_KB * TC_MAXKB && p.H >= 2 && p.W >= 2;
+}
+
+size_t corr_tc_workspace_bytes(const CorrParams &p) {
+    return corr_tc_supported(p) ? (size_t)4 * p.B * p.C * p.H * p.W * sizeof(__nv_bfloat16) : 0;
+}
+
+static int make_class_map(CUtensorMap *m, const void *base, const CorrParams &p, int box_w, int box_h) {
+    const int Hc = p.H / 2, Wc = p.W / 2;
+    uint64_t dims[4] = {(uint64_t)p.C, (uint64_t)Wc, (uint64_t)Hc, (uint64_t)p.B * 4};
+    uint64_t strides[3] = {(uint64_t)p.C * 2, (uint64_t)Wc * p.C * 2, (uint64_t)Hc * Wc * p.C * 2};
+    uint32_t box[4] = {(uint32_t)TC_KB, (uint32_t)box_w, (uint32_t)box_h, 1u};
+    return make_tensor_map_bf16_sw128(m, base, 4, dims, strides, box);
+}
+
+int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrParams &p, void *workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
+    const size_t need = corr_tc_workspace_bytes(p);
+    if (need == 0) return fail(FN2B200_EUNSUPPORTED, "correlation_forward(tc): configuration not supported");
+    if (!workspace || workspace_bytes < need)
+        return fail(FN2B200_EINVAL, "correlation_forward(tc): workspace of %zu bytes required, got %zu", need,
+                    workspace_bytes);
+    if (reinterpret_cast<uintptr_t>(workspace) & 127)
+        return fail(FN2B200_EINVAL, "correlation_forward(tc): workspace must be 128-byte aligned");
+    const size_t per = (size_t)p.B * p.C * p.H * p.W;
+    __nv_bfloat16 *w = static_cast<__nv_bfloat16 *>(workspace);
+    __nv_bfloat16 *h1 = w, *l1 = w + per, *h2 = w + 2 * per, *l2 = w + 3 * per;
+    dim3 sgrid((p.W + 63) / 64, p.C / 64, p.B * p.H);
+    corr_tc_split_kernel<<<sgrid, 256, 0, st>>>(in1, h1, l1, p.C, p.H, p.W);
+    corr_tc_split_kernel<<<sgrid, 256, 0, st>>>(in2, h2, l2, p.C, p.H, p.W);
+    count_launch(2);
+    int rc = check_launch("correlation_forward(tc split)");
+    if (rc) return rc;
+
+    CUtensorMap m1h, m1l, m2h, m2l;
+    if ((rc = make_class_map(&m1h, h1, p, TC_TW, TC_TH))) return rc;
+    if ((rc = make_class_map(&m1l, l1, p, TC_TW, TC_TH))) return rc;
+    if ((rc = make_class_map(&m2h, h2, p, TC_HW, TC_UR))) return rc;
+    if ((rc = make_class_map(&m2l, l2, p, TC_HW, TC_UR))) return rc;
+
+    const int Hc = p.H / 2, Wc = p.W / 2;
+    const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
+    const int ntiles = p.B * 4 * nxt * nyt;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e != cudaSuccess) return fail((int)e, "correlation_forward(tc): smem attribute (%s)", cudaGetErrorString(e));
+    const int grid = ntiles < sms ? ntiles : sms;
+    corr_fwd_tc_kernel<<<grid, 192, TC_SMEM, st>>>(m1h, m1l, m2h, m2l, out, p.B, p.C, p.H, p.W, ntiles);
+    count_launch();
+    return check_launch("correlation_forward(tc)");
+}
+
+}  // namespace fn2

@@ -59,9 +59,20 @@ def correlation_forward(input1, input2, pad_size, kernel_size, max_displacement,
     with torch.cuda.device_of(a):
         if out is None:
             out = torch.empty((B, D, oH, oW), dtype=torch.float32, device=a.device)
-        check(LIB.fn2b200_correlation_forward(_ptr(a), _ptr(b), _ptr(out), B, C, H, W, pad_size, kernel_size,
-                                              max_displacement, stride1, stride2, int(corr_multiply), _stream(a)),
-              "correlation_forward")
+        ws_bytes = int(LIB.fn2b200_correlation_forward_workspace(B, C, H, W, pad_size, kernel_size, max_displacement,
+                                                                 stride1, stride2))
+        if ws_bytes:
+            # scratch for the tensor-core path's bf16 hi/lo operands (the analogue of the reference's
+            # rbot1/rbot2, correlation.py:20-21); the caching allocator keeps it stream-ordered
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+            check(LIB.fn2b200_correlation_forward_ws(_ptr(a), _ptr(b), _ptr(out), B, C, H, W, pad_size, kernel_size,
+                                                     max_displacement, stride1, stride2, int(corr_multiply),
+                                                     _ptr(ws), ws_bytes, _stream(a)),
+                  "correlation_forward")
+        else:
+            check(LIB.fn2b200_correlation_forward(_ptr(a), _ptr(b), _ptr(out), B, C, H, W, pad_size, kernel_size,
+                                                  max_displacement, stride1, stride2, int(corr_multiply), _stream(a)),
+                  "correlation_forward")
     return out
 
 

@@ -68,6 +68,23 @@ int fn2b200_correlation_forward(const float *input1, const float *input2, float 
                                 int corr_type_multiply, void *stream);
 
 /*
+ * Tensor-core forward (tcgen05, bf16 hi/lo operand split, fp32 accumulation in TMEM; error ~1e-5
+ * relative, inside the 1e-4 contract).  It needs scratch for the split operands:
+ * fn2b200_correlation_forward_workspace() returns the bytes required (0 = this configuration runs
+ * on the FP32-FMA kernels; set the environment variable FN2B200_CORR_FWD=fma to force that), and
+ * fn2b200_correlation_forward_ws() is fn2b200_correlation_forward() plus a 128-byte-aligned device
+ * workspace of at least that size (NULL / too small -> the FMA kernels).  The workspace plays the
+ * role of the reference's rInput1/rInput2 scratch tensors (correlation_cuda.cc:36-41) and may be
+ * reused or freed (stream-ordered) as soon as the call returns.
+ */
+size_t fn2b200_correlation_forward_workspace(int B, int C, int H, int W, int pad_size, int kernel_size,
+                                             int max_displacement, int stride1, int stride2);
+int fn2b200_correlation_forward_ws(const float *input1, const float *input2, float *output, int B, int C,
+                                   int H, int W, int pad_size, int kernel_size, int max_displacement,
+                                   int stride1, int stride2, int corr_type_multiply, void *workspace,
+                                   size_t workspace_bytes, void *stream);
+
+/*
  * grad_output: [B,D,oH,oW]; grad_input1, grad_input2: [B,C,H,W] (either may be NULL to skip it).
  * stride1 must be 1 (the reference's backward indexes out of bounds otherwise,
  * correlation_cuda_kernel.cu:163-164 vs :520) -> FN2B200_EUNSUPPORTED.
@@ -112,7 +129,8 @@ int fn2b200_channelnorm_backward(const float *input1, const float *output,
 
 /*
  * Introspection for benchmarks/tests: which kernel family the correlation entry points would
- * dispatch to for these parameters.  0 = generic gather kernels, 1 = TMA-tiled FMA kernels.
+ * dispatch to for these parameters.  0 = generic gather kernels, 1 = TMA-tiled FMA kernels,
+ * 2 = forward on tensor cores (when a workspace is supplied) + TMA-tiled FMA backward.
  */
 int fn2b200_correlation_path(int C, int H, int W, int pad_size, int kernel_size,
                              int max_displacement, int stride1, int stride2);

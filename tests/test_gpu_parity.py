@@ -31,10 +31,14 @@ def _randn(shape, seed, scale=1.0):
 # ------------------------------------------------------------------------------------------------
 CORR_CASES = [
     # (pad, k, md, s1, s2), (B, C, H, W), expected path (1 = TMA-tiled, 0 = generic)
-    ((20, 1, 20, 1, 2), (1, 256, 48, 64), 1),     # BASELINE cfg1
+    ((20, 1, 20, 1, 2), (1, 256, 48, 64), 2),     # BASELINE cfg1 (tensor-core forward)
+    ((20, 1, 20, 1, 2), (2, 64, 10, 36), 2),      # tc: ragged tiles (Hc=5, Wc=18)
+    ((20, 1, 20, 1, 2), (1, 128, 2, 2), 2),       # tc: a single class pixel per class
+    ((20, 1, 20, 1, 2), (1, 192, 30, 70), 2),     # tc: 3 k-blocks, Wc=35 odd
+    ((21, 1, 21, 1, 2), (1, 64, 12, 20), 2),      # tc: md=21 -> dr=10, pad == md
     ((20, 1, 20, 1, 2), (2, 20, 13, 192), 1),     # odd H, C % 8 != 0, 1.5 tiles wide
     ((20, 1, 20, 1, 2), (1, 3, 5, 8), 1),         # tiny: W < tile, H < row quad
-    ((20, 1, 20, 1, 2), (1, 64, 9, 260), 1),      # 3 tiles wide, ragged last tile
+    ((20, 1, 20, 1, 2), (1, 64, 9, 260), 1),      # 3 tiles wide, ragged last tile (odd H -> FMA path)
     ((24, 1, 20, 1, 2), (1, 16, 10, 32), 1),      # pad > md (output larger than input), tiled
     ((16, 1, 20, 1, 2), (1, 16, 14, 32), 1),      # pad < md (output smaller), tiled
     ((22, 1, 20, 1, 2), (1, 16, 10, 32), 0),      # (md - pad) % 4 != 0 -> generic (TMA start alignment)
@@ -65,6 +69,23 @@ def test_correlation_vs_oracle(params, shape, path):
     r1, r2 = orc.correlation_backward(a.numpy(), b.numpy(), go.numpy(), pad, k, md, s1, s2)
     assert_close(g1.cpu().numpy(), r1, TOL, "corr gI1 %s %s" % (params, shape))
     assert_close(g2.cpu().numpy(), r2, TOL, "corr gI2 %s %s" % (params, shape))
+
+
+def test_correlation_tc_matches_fma_path(monkeypatch):
+    """The tensor-core forward (bf16 hi/lo split) against the FP32-FMA forward on the same input."""
+    f = _f2()
+    a, b = _randn((2, 256, 24, 40), 50).cuda(), _randn((2, 256, 24, 40), 51).cuda()
+    out_tc = f.functional.correlation_forward(a, b, 20, 1, 20, 1, 2)
+    monkeypatch.setenv("FN2B200_CORR_FWD", "fma")
+    assert f._lib.LIB.fn2b200_correlation_path(256, 24, 40, 20, 1, 20, 1, 2) == 1
+    out_fma = f.functional.correlation_forward(a, b, 20, 1, 20, 1, 2)
+    monkeypatch.delenv("FN2B200_CORR_FWD")
+    assert f._lib.LIB.fn2b200_correlation_path(256, 24, 40, 20, 1, 20, 1, 2) == 2
+    e = rel_err(out_tc.cpu().numpy(), out_fma.cpu().numpy())
+    assert 0 < e < 5e-5, e          # different arithmetic (not bit-identical), far inside 1e-4
+    # badly scaled inputs: the hi/lo split must not lose the small operand
+    out_tc = f.functional.correlation_forward(a * 1e-3, b * 3e4, 20, 1, 20, 1, 2)
+    assert rel_err(out_tc.cpu().numpy(), (out_fma * 30.0).cpu().numpy()) < 5e-5
 
 
 def test_correlation_stride1_2_forward_only():
