@@ -71,7 +71,8 @@ def test_out_shape_and_path_queries():
     assert LIB.fn2b200_correlation_forward_workspace(8, 256, 112, 256, 20, 1, 20, 1, 2) == 8 * 8 * 256 * 112 * 256
     assert LIB.fn2b200_correlation_forward_workspace(8, 20, 112, 256, 20, 1, 20, 1, 2) == 0
     assert LIB.fn2b200_correlation_path(256, 112, 256, 20, 3, 20, 1, 2) == 0   # kernel_size 3 -> generic
-    assert LIB.fn2b200_correlation_path(256, 112, 250, 20, 1, 20, 1, 2) == 0   # W % 4 != 0 -> generic
+    assert LIB.fn2b200_correlation_path(256, 112, 250, 20, 1, 20, 1, 2) == 2   # even W is enough for the tc forward
+    assert LIB.fn2b200_correlation_path(256, 112, 251, 20, 1, 20, 1, 2) == 0   # odd W -> generic
     assert LIB.fn2b200_correlation_path(256, 112, 256, 22, 1, 20, 1, 2) == 0   # (md-pad) % 4 != 0 -> generic
     assert LIB.fn2b200_correlation_path(256, 112, 256, 24, 1, 20, 1, 2) == 1
 
