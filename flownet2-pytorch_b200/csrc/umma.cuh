@@ -21,11 +21,35 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// K-major operand WITHOUT swizzle ("interleave"): 8-row x 16-byte core matrices stored contiguously
+// (128 B each).  One K=16 MMA step reads 2 core-matrix columns: LBO = byte distance between the two
+// 16-byte K chunks, SBO = byte distance between consecutive 8-row groups.  layout type 0.
+__device__ __forceinline__ uint64_t umma_desc_k_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// MN-major operand, 128-byte swizzle: rows are K (128 B = 64 contiguous MN elements each); 8-row
+// groups are SBO = 1024 B apart, successive 64-element MN blocks LBO bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 // ---- instruction descriptor (32-bit) for kind::f16: BF16 x BF16 -> FP32, both operands K-major --
 //  [4,6) D format (1 = F32)  [7,10) A format (1 = BF16)  [10,13) B format (1 = BF16)
 //  [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3  [24,29) M >> 4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N, int b_mn_major = 0) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(b_mn_major & 1) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
 
 #ifdef __CUDACC__

@@ -2,6 +2,7 @@
 // D[128 x N] (fp32) = A[128 x K] * B[N x K]^T with bf16 operands, K a multiple of 64, N = 144.
 // Exposed as fn2b200_debug_umma_gemm (tests/test_gpu_umma.py compares with a CPU product).
 #include "umma.cuh"
+#include <cuda_bf16.h>
 
 namespace fn2 {
 
@@ -79,6 +80,92 @@ int umma_selftest(const void *A, const void *B, float *D, int K, cudaStream_t st
     umma_selftest_kernel<<<1, 128, smem, st>>>(ma, mb, D, K);
     count_launch();
     return check_launch("umma_selftest");
+}
+
+}  // namespace fn2
+
+// ------------------------------------------------------------------------------------------------
+// Variant 2 (the backward kernel's operand forms): D[128 x 64] = A[128 x K] * Bt[K x 64] with
+//   A : K-major, NO swizzle, written to shared memory by the threads themselves (core-matrix layout)
+//   Bt: MN-major (N contiguous), SW128, loaded by TMA from a row-major [K][64] bf16 matrix.
+// K = 144 (9 k-steps), like one unit of the backward kernel.
+// ------------------------------------------------------------------------------------------------
+namespace fn2 {
+
+constexpr int ST2_K = 144, ST2_N = 64;
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest2_kernel(const __nv_bfloat16_raw *__restrict__ A, const __grid_constant__ CUtensorMap mapB,
+                      float *__restrict__ D) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sB = smem;                              // [144 rows(K)][128 B], SW128 (MN-major)
+    unsigned char *sA = smem + ST2_K * 128;                // 9 k-steps x [2 chunks][16 groups][8 rows x 16 B]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + 9 * 4096);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<64>(tmem_slot);
+    // every thread writes its own row of A into the no-swizzle core-matrix layout
+    {
+        const int p = tid;
+        const unsigned short *arow = reinterpret_cast<const unsigned short *>(A) + (size_t)p * ST2_K;
+        for (int k = 0; k < ST2_K; ++k) {
+            const int ks = k >> 4, c = (k >> 3) & 1, e = k & 7;
+            *reinterpret_cast<unsigned short *>(sA + ks * 4096 + c * 2048 + (p >> 3) * 128 + (p & 7) * 16 + e * 2) = arow[k];
+        }
+    }
+    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bars[0], ST2_K * 128);
+        tma_load_2d(sB, &mapB, &bars[0], 0, 0);
+        mbar_wait(&bars[0], 0);
+        tcgen05_fence_after();
+        const uint32_t idesc = umma_idesc_bf16_f32(128, ST2_N, 1);
+        const uint64_t db = umma_desc_mn_sw128(smem_u32(sB), ST2_K * 128);
+#pragma unroll
+        for (int ks = 0; ks < ST2_K / 16; ++ks) {
+            const uint64_t da = umma_desc_k_noswz(smem_u32(sA + ks * 4096), 2048, 128);
+            umma_bf16_ss(tmem_base, da, db + (uint64_t)((ks * 16 * 128) >> 4), idesc, ks != 0);
+        }
+        umma_commit(&bars[1]);
+        mbar_wait(&bars[1], 0);
+    }
+    __syncthreads();
+    tcgen05_fence_after();
+    for (int c0 = 0; c0 < ST2_N; c0 += 16) {
+        float r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) D[tid * ST2_N + c0 + j] = r[j];
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<64>(tmem_base);
+}
+
+int umma_selftest2(const void *A, const void *Bt, float *D, cudaStream_t st) {
+    CUtensorMap mb;
+    uint64_t dims[2] = {ST2_N, ST2_K};
+    uint64_t str[1] = {ST2_N * 2};
+    uint32_t box[2] = {ST2_N, ST2_K};
+    int rc = make_tensor_map_bf16_sw128(&mb, Bt, 2, dims, str, box);
+    if (rc) return rc;
+    const int smem = ST2_K * 128 + 9 * 4096 + 1024 + 64;
+    cudaError_t e = cudaFuncSetAttribute(umma_selftest2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail((int)e, "umma_selftest2: smem attribute (%s)", cudaGetErrorString(e));
+    umma_selftest2_kernel<<<1, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16_raw *>(A), mb, D);
+    count_launch();
+    return check_launch("umma_selftest2");
 }
 
 }  // namespace fn2

@@ -138,7 +138,10 @@ int fn2b200_correlation_path(int C, int H, int W, int pad_size, int kernel_size,
 /*
  * Hardware self-test of the tcgen05 / TMEM / TMA-swizzle plumbing the tensor-core correlation path
  * is built on: D[128 x 144] (fp32, row-major) = A[128 x K] * B[144 x K]^T, A and B bf16 row-major
- * device buffers, K a multiple of 64.  Test hook only (tests/test_gpu_umma.py).
+ * device buffers, K a multiple of 64.  K == -144 selects the second form (the backward kernel's
+ * operand layouts): D[128 x 64] = A[128 x 144] * Bt[144 x 64], A written to shared memory by the
+ * threads in the no-swizzle core-matrix layout, Bt ([K][N] row-major) loaded as an MN-major
+ * SW128 operand.  Test hook only (tests/test_gpu_umma.py).
  */
 int fn2b200_debug_umma_gemm(const void *A_bf16, const void *B_bf16, float *D, int K, void *stream);
 

@@ -23,3 +23,21 @@ def test_umma_gemm_matches_cpu(K):
     ref = A.double() @ B.double().t()
     err = (D.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-5, err
+
+
+def test_umma_gemm_noswizzle_a_mnmajor_b():
+    """Operand forms of the tensor-core backward: A built by threads (K-major, no swizzle),
+    B^T = [K][N] row-major consumed as an MN-major SW128 operand."""
+    from flownet2_b200._lib import LIB, check
+    g = torch.Generator().manual_seed(7)
+    A = torch.randn(128, 144, generator=g).bfloat16()
+    Bt = torch.randn(144, 64, generator=g).bfloat16()
+    Ad, Bd = A.cuda(), Bt.cuda()
+    D = torch.full((128, 64), float("nan"), device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(LIB.fn2b200_debug_umma_gemm(ctypes.c_void_p(Ad.data_ptr()), ctypes.c_void_p(Bd.data_ptr()),
+                                      ctypes.c_void_p(D.data_ptr()), -144, st), "debug_umma_gemm(2)")
+    torch.cuda.synchronize()
+    ref = A.double() @ Bt.double()
+    err = (D.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err
