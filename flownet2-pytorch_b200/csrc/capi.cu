@@ -147,6 +147,10 @@ static bool tc_enabled() {
     const char *e = getenv("FN2B200_CORR_FWD");
     return !(e && (e[0] == 'f' || e[0] == 'F'));
 }
+static bool tc_bwd_enabled() {
+    const char *e = getenv("FN2B200_CORR_BWD");
+    return !(e && (e[0] == 'f' || e[0] == 'F'));
+}
 
 }  // namespace fn2
 
@@ -243,6 +247,33 @@ int fn2b200_correlation_backward(const float *in1, const float *in2, const float
     cudaStream_t st = (cudaStream_t)stream;
     if (corr_tiled_supported(p)) return corr_backward_tiled(in1, in2, gout, gin1, gin2, p, st);
     return corr_backward_generic(in1, in2, gout, gin1, gin2, p, st);
+}
+
+size_t fn2b200_correlation_backward_workspace(int B, int C, int H, int W, int pad, int k, int md, int s1,
+                                              int s2) {
+    CorrParams p;
+    if (fill_corr_params(p, B, C, H, W, pad, k, md, s1, s2)) return 0;
+    if (!tc_bwd_enabled()) return 0;
+    return corr_tc_workspace_bytes(p);
+}
+
+int fn2b200_correlation_backward_ws(const float *in1, const float *in2, const float *gout, float *gin1,
+                                    float *gin2, int B, int C, int H, int W, int pad, int k, int md, int s1,
+                                    int s2, int corr_type_multiply, void *workspace, size_t workspace_bytes,
+                                    int workspace_has_split, void *stream) {
+    CorrParams p;
+    int rc = fill_corr_params(p, B, C, H, W, pad, k, md, s1, s2);
+    if (rc) return rc;
+    if (workspace && tc_bwd_enabled() && corr_tc_supported(p) && workspace_bytes >= corr_tc_workspace_bytes(p)) {
+        if (B == 0) return 0;
+        if (!in1 || !in2 || !gout) return fail(FN2B200_ENULL, "correlation_backward: null pointer");
+        if (!gin1 && !gin2) return 0;
+        if ((rc = bind_device_of(in1))) return rc;
+        return corr_backward_tc(in1, in2, gout, gin1, gin2, p, workspace, workspace_bytes, workspace_has_split,
+                                (cudaStream_t)stream);
+    }
+    return fn2b200_correlation_backward(in1, in2, gout, gin1, gin2, B, C, H, W, pad, k, md, s1, s2,
+                                        corr_type_multiply, stream);
 }
 
 static int check_resample(const char *who, const int64_t *istride, int B, int C, int iH, int iW,

@@ -137,6 +137,8 @@ int corr_backward_tiled(const float *in1, const float *in2, const float *gout, f
 // Tensor-core (tcgen05) forward for FlowNetC's configuration; needs a caller-provided workspace.
 bool corr_tc_supported(const CorrParams &p);
 size_t corr_tc_workspace_bytes(const CorrParams &p);
+int corr_backward_tc(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
+                     const CorrParams &p, void *workspace, size_t workspace_bytes, int have_split, cudaStream_t st);
 int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrParams &p, void *workspace,
                     size_t workspace_bytes, cudaStream_t st);
 

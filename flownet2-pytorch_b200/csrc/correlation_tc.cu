@@ -50,37 +50,50 @@ constexpr int TC_SMEM = TC_SMEM_A + TC_SMEM_B + TC_SMEM_E + TC_NBAR * 8 + 16 + 1
 // Prepass: NCHW fp32 -> parity-class-separated NHWC bf16 hi / lo
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-corr_tc_split_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ hi,
-                     __nv_bfloat16 *__restrict__ lo, int C, int H, int W) {
+corr_tc_split_kernel(const float *__restrict__ in0, const float *__restrict__ in1,
+                     __nv_bfloat16 *__restrict__ hi0, __nv_bfloat16 *__restrict__ lo0,
+                     __nv_bfloat16 *__restrict__ hi1, __nv_bfloat16 *__restrict__ lo1, int C, int H, int W) {
     __shared__ float tile[64][65];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int ncb = C / 64;
+    const int which = blockIdx.y / ncb, c0 = (blockIdx.y % ncb) * 64;
+    const float *__restrict__ in = which ? in1 : in0;
+    __nv_bfloat16 *__restrict__ hi = which ? hi1 : hi0;
+    __nv_bfloat16 *__restrict__ lo = which ? lo1 : lo0;
+    const int x0 = blockIdx.x * 64;
     const int n = blockIdx.z / H, y = blockIdx.z % H;
     const int Hc = H >> 1, Wc = W >> 1;
     {
         const int xo = tid & 63, cs = tid >> 6;
         const float *src = in + (((long)n * C + c0) * H + y) * W + x0 + xo;
         const bool ok = x0 + xo < W;
-#pragma unroll 4
+#pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int c = i * 4 + cs;
             tile[c][xo] = ok ? ldg_stream1(src + (long)c * H * W) : 0.f;
         }
     }
     __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int xo = warp * 8 + j, x = x0 + xo;
-        if (x >= W) break;
+    // thread -> (pixel, 16 channels): 4 threads write one pixel's 128 contiguous bytes (hi) + 128 (lo)
+    const int xo = tid >> 2, cg = tid & 3, x = x0 + xo;
+    if (x < W) {
         const int cls = (y & 1) * 2 + (x & 1);
-        const long row = (((long)(n * 4 + cls) * Hc + (y >> 1)) * Wc + (x >> 1)) * C + c0 + 2 * lane;
-        const float v0 = tile[2 * lane][xo], v1 = tile[2 * lane + 1][xo];
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-        *reinterpret_cast<__nv_bfloat162 *>(hi + row) = __halves2bfloat162(h0, h1);
-        *reinterpret_cast<__nv_bfloat162 *>(lo + row) = __halves2bfloat162(l0, l1);
+        const long row = (((long)(n * 4 + cls) * Hc + (y >> 1)) * Wc + (x >> 1)) * C + c0 + cg * 16;
+        uint32_t hw[8], lw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float v0 = tile[cg * 16 + 2 * i][xo], v1 = tile[cg * 16 + 2 * i + 1][xo];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+            hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        uint4 *ph = reinterpret_cast<uint4 *>(hi + row), *pl = reinterpret_cast<uint4 *>(lo + row);
+        ph[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        ph[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        pl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        pl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
     }
 }
 
@@ -244,6 +257,215 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// Backward on tensor cores.  WHICH == 1: gradInput1 (other = input2), WHICH == 2: gradInput2.
+//
+//   gI1[c, p] = 1/C sum_q G1[p, q] f2[c, q],   G1[p, q] = gO[(q - p), p]          (|q - p| <= 10)
+//   gI2[c, q] = 1/C sum_p G2[q, p] f1[c, p],   G2[q, p] = gO[(q - p), p]
+// per parity class: D[128 tile px][C] += A[128][144] * B[144 halo px][C] over the 7 halo-row units,
+// accumulated in ONE TMEM buffer per tile (C <= 256 fp32 columns, double-buffered across tiles).
+//   A = the banded gradOutput matrix, built per unit by 4 "builder" warps straight from the fp32
+//       gradOutput planes (bf16 hi/lo split on the fly) into the no-swizzle K-major core-matrix layout;
+//   B = the other input's halo chunk from the prepass copy ([pixel][channel] bf16 = MN-major operand),
+//       one 64-channel block per TMA stage;
+//   3 MMAs (hi*hi, hi*lo, lo*hi) per k-step, N = 64 per instruction.
+// Roles (320 threads): warp 0 TMA, warp 1 MMA, warps 2-5 builders, warps 6-9 epilogue.
+// ------------------------------------------------------------------------------------------------
+constexpr int TB_KS = TC_N / 16;                   // 9 k-steps per unit
+constexpr int TB_AHL = TB_KS * 4096;               // 36864 B: one of {hi, lo} of a unit's A
+constexpr int TB_ASTG = 2 * TB_AHL;                // 73728 B per A stage
+constexpr int TB_NAST = 2, TB_NBST = 2, TB_NACC = 2;
+constexpr int TB_SMEM_A = TB_NAST * TB_ASTG;       // 147456
+constexpr int TB_SMEM_B = TB_NBST * 2 * TC_BBLK;   // 73728
+constexpr int TB_NBAR = 2 * TB_NAST + 2 * TB_NBST + 2 * TB_NACC;
+constexpr int TB_SMEM = TB_SMEM_A + TB_SMEM_B + TB_NBAR * 8 + 16 + 1024;
+
+template <int WHICH>
+__global__ void __launch_bounds__(320, 1)
+corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constant__ CUtensorMap mol,
+                   const float *__restrict__ gout, float *__restrict__ gin, int B, int C, int H, int W,
+                   int ntiles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sA = smem;                          // [stage][hl][9 k-steps][2 chunks][16 groups][8 x 16 B]
+    unsigned char *sB = smem + TB_SMEM_A;              // [stage][hl][144 rows x 128 B] (SW128)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TB_SMEM_B);
+    uint64_t *a_full = bars, *a_empty = a_full + TB_NAST;
+    uint64_t *b_full = a_empty + TB_NAST, *b_empty = b_full + TB_NBST;
+    uint64_t *acc_full = b_empty + TB_NBST, *acc_empty = acc_full + TB_NACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + TB_NBAR);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Hc = H >> 1, Wc = W >> 1;
+    const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
+    const int ncb = C / TC_KB;
+    const long plane = (long)H * W;
+
+    if (tid == 0) {
+        prefetch_tensormap(&moh); prefetch_tensormap(&mol);
+        for (int i = 0; i < TB_NAST; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < TB_NBST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < TB_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: the other input's halo chunks =====================
+        if (lane == 0) {
+            uint32_t bcount = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const TcTile T = tc_decode(t, nxt, nyt);
+                const int img = T.n * 4 + T.py * 2 + T.px;
+                for (int u = 0; u < TC_NU; ++u)
+                    for (int j = 0; j < ncb; ++j, ++bcount) {
+                        const int s = bcount % TB_NBST;
+                        mbar_wait(&b_empty[s], ((bcount / TB_NBST) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&b_full[s], 2 * TC_BBLK);
+                        tma_load_4d(sB + (s * 2 + 0) * TC_BBLK, &moh, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
+                                    T.yc0 - TC_DR + u * TC_UR, img);
+                        tma_load_4d(sB + (s * 2 + 1) * TC_BBLK, &mol, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
+                                    T.yc0 - TC_DR + u * TC_UR, img);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_f32(128, TC_KB, 1);   // N = 64, B MN-major
+            uint32_t bcount = 0, ucount = 0, tcount = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
+                const int ab = tcount % TB_NACC;
+                mbar_wait(&acc_empty[ab], ((tcount / TB_NACC) & 1) ^ 1);
+                tcgen05_fence_after();
+                for (int u = 0; u < TC_NU; ++u, ++ucount) {
+                    const int as = ucount % TB_NAST;
+                    mbar_wait(&a_full[as], (ucount / TB_NAST) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t a_hi = smem_u32(sA + as * TB_ASTG), a_lo = a_hi + TB_AHL;
+                    for (int j = 0; j < ncb; ++j, ++bcount) {
+                        const int s = bcount % TB_NBST;
+                        mbar_wait(&b_full[s], (bcount / TB_NBST) & 1);
+                        tcgen05_fence_after();
+                        const uint64_t bh = umma_desc_mn_sw128(smem_u32(sB + (s * 2 + 0) * TC_BBLK), TC_BBLK);
+                        const uint64_t bl = umma_desc_mn_sw128(smem_u32(sB + (s * 2 + 1) * TC_BBLK), TC_BBLK);
+                        const uint32_t d = tmem_base + ab * 256 + j * TC_KB;
+#pragma unroll
+                        for (int ks = 0; ks < TB_KS; ++ks) {
+                            const uint64_t ah = umma_desc_k_noswz(a_hi + ks * 4096, 2048, 128);
+                            const uint64_t al = umma_desc_k_noswz(a_lo + ks * 4096, 2048, 128);
+                            const uint64_t kadv = (uint64_t)((ks * 16 * 128) >> 4);
+                            umma_bf16_ss(d, ah, bh + kadv, idesc, (u | ks) != 0);
+                            umma_bf16_ss(d, ah, bl + kadv, idesc, 1);
+                            umma_bf16_ss(d, al, bh + kadv, idesc, 1);
+                        }
+                        umma_commit(&b_empty[s]);
+                    }
+                    umma_commit(&a_empty[as]);
+                }
+                umma_commit(&acc_full[ab]);
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== builders: banded gradOutput matrix A (hi / lo) =====================
+        const int p = tid - 64;
+        const int py_t = p >> 4, px_t = p & 15;
+        const uint32_t row_off = (p >> 3) * 128 + (p & 7) * 16;
+        uint32_t ucount = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const TcTile T = tc_decode(t, nxt, nyt);
+            const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
+            const bool pix_ok = (yc < Hc) && (xc < Wc);
+            const float *gn = gout + (long)T.n * (TC_DS * TC_DS) * plane;
+            for (int u = 0; u < TC_NU; ++u, ++ucount) {
+                const int as = ucount % TB_NAST;
+                mbar_wait(&a_empty[as], ((ucount / TB_NAST) & 1) ^ 1);
+                unsigned char *ah = sA + as * TB_ASTG + row_off, *al = ah + TB_AHL;
+#pragma unroll
+                for (int i = 0; i < 2 * TB_KS; ++i) {           // zero this thread's row (18 x 16 B, hi and lo)
+                    *reinterpret_cast<uint4 *>(ah + i * 2048) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(al + i * 2048) = make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll 1
+                for (int hrl = 0; hrl < TC_UR; ++hrl) {
+                    const int tjp = u * TC_UR + hrl - py_t;       // tj + 10 of this (pixel row, halo row) pair
+                    if (tjp < 0 || tjp >= TC_DS) continue;
+                    const float *src;
+                    long step;
+                    bool row_ok;
+                    int xs0;
+                    if (WHICH == 1) {
+                        row_ok = pix_ok;                          // gO at the output pixel itself
+                        src = gn + (long)(tjp * TC_DS) * plane + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
+                        step = plane;                             // next ti -> next plane
+                        xs0 = 0;
+                    } else {
+                        const int ycs = T.yc0 - TC_DR + u * TC_UR + hrl;   // source pixel row (class coords)
+                        row_ok = (ycs >= 0) && (ycs < Hc);
+                        xs0 = T.xc0 - TC_DR + px_t;                        // source column for j = 0
+                        // plane (20 - tjp, 20 - j), pixel (ycs, xs0 + j): j -> j+1 moves -1 plane, +2 in x
+                        src = gn + (long)((TC_DS - 1 - tjp) * TC_DS + (TC_DS - 1)) * plane +
+                              (long)(2 * ycs + T.py) * W + (2 * xs0 + T.px);
+                        step = 2 - plane;
+                    }
+                    if (!row_ok) continue;
+#pragma unroll
+                    for (int j = 0; j < TC_DS; ++j) {
+                        float v;
+                        if (WHICH == 1) v = __ldg(src + j * step);
+                        else v = (xs0 + j >= 0 && xs0 + j < Wc) ? __ldg(src + j * step) : 0.f;
+                        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+                        const int k = hrl * TC_HW + px_t + j;
+                        const uint32_t off = (k >> 4) * 4096 + ((k >> 3) & 1) * 2048 + (k & 7) * 2;
+                        *reinterpret_cast<unsigned short *>(ah + off) = __bfloat16_as_ushort(h);
+                        *reinterpret_cast<unsigned short *>(al + off) = __bfloat16_as_ushort(l);
+                    }
+                }
+                fence_proxy_async();          // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(&a_full[as]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 6..9) =====================
+        const int quad = warp & 3;
+        const int p = quad * 32 + lane;
+        const int py_t = p >> 4, px_t = p & 15;
+        const float nelems = (float)C;
+        uint32_t tcount = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
+            const TcTile T = tc_decode(t, nxt, nyt);
+            const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
+            const bool pix_ok = (yc < Hc) && (xc < Wc);
+            float *o = gin + (long)T.n * C * plane + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
+            const int ab = tcount % TB_NACC;
+            mbar_wait(&acc_full[ab], (tcount / TB_NACC) & 1);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ab * 256;
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                float r[32];
+                tmem_ld16(taddr + c0, r);
+                tmem_ld16(taddr + c0 + 16, r + 16);
+                tmem_ld_wait();
+                if (pix_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[(long)(c0 + i) * plane] = r[i] / nelems;
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(&acc_empty[ab]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
 bool corr_tc_supported(const CorrParams &p) {
@@ -253,6 +475,15 @@ bool corr_tc_supported(const CorrParams &p) {
 
 size_t corr_tc_workspace_bytes(const CorrParams &p) {
     return corr_tc_supported(p) ? (size_t)4 * p.B * p.C * p.H * p.W * sizeof(__nv_bfloat16) : 0;
+}
+
+// workspace layout: [hi(in1) | lo(in1) | hi(in2) | lo(in2)], each B*C*H*W bf16
+static int corr_tc_split(const float *in1, const float *in2, __nv_bfloat16 *w, const CorrParams &p, cudaStream_t st) {
+    const size_t per = (size_t)p.B * p.C * p.H * p.W;
+    dim3 sgrid((p.W + 63) / 64, 2 * (p.C / 64), p.B * p.H);
+    corr_tc_split_kernel<<<sgrid, 256, 0, st>>>(in1, in2, w, w + per, w + 2 * per, w + 3 * per, p.C, p.H, p.W);
+    count_launch();
+    return check_launch("correlation(tc split)");
 }
 
 static int make_class_map(CUtensorMap *m, const void *base, const CorrParams &p, int box_w, int box_h) {
@@ -275,11 +506,7 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrPa
     const size_t per = (size_t)p.B * p.C * p.H * p.W;
     __nv_bfloat16 *w = static_cast<__nv_bfloat16 *>(workspace);
     __nv_bfloat16 *h1 = w, *l1 = w + per, *h2 = w + 2 * per, *l2 = w + 3 * per;
-    dim3 sgrid((p.W + 63) / 64, p.C / 64, p.B * p.H);
-    corr_tc_split_kernel<<<sgrid, 256, 0, st>>>(in1, h1, l1, p.C, p.H, p.W);
-    corr_tc_split_kernel<<<sgrid, 256, 0, st>>>(in2, h2, l2, p.C, p.H, p.W);
-    count_launch(2);
-    int rc = check_launch("correlation_forward(tc split)");
+    int rc = corr_tc_split(in1, in2, w, p, st);
     if (rc) return rc;
 
     CUtensorMap m1h, m1l, m2h, m2l;
@@ -300,6 +527,45 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrPa
     corr_fwd_tc_kernel<<<grid, 192, TC_SMEM, st>>>(m1h, m1l, m2h, m2l, out, p.B, p.C, p.H, p.W, ntiles);
     count_launch();
     return check_launch("correlation_forward(tc)");
+}
+
+template <int WHICH>
+static int launch_bwd_tc(const __nv_bfloat16 *oh, const __nv_bfloat16 *ol, const float *gout, float *gin,
+                         const CorrParams &p, cudaStream_t st) {
+    CUtensorMap moh, mol;
+    int rc;
+    if ((rc = make_class_map(&moh, oh, p, TC_HW, TC_UR))) return rc;
+    if ((rc = make_class_map(&mol, ol, p, TC_HW, TC_UR))) return rc;
+    const int Hc = p.H / 2, Wc = p.W / 2;
+    const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
+    const int ntiles = p.B * 4 * nxt * nyt;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto kern = corr_bwd_tc_kernel<WHICH>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
+    if (e != cudaSuccess) return fail((int)e, "correlation_backward(tc): smem attribute (%s)", cudaGetErrorString(e));
+    const int grid = ntiles < sms ? ntiles : sms;
+    kern<<<grid, 320, TB_SMEM, st>>>(moh, mol, gout, gin, p.B, p.C, p.H, p.W, ntiles);
+    count_launch();
+    return check_launch("correlation_backward(tc)");
+}
+
+// have_split != 0: the workspace already holds the hi/lo copies of (in1, in2) written by
+// corr_forward_tc on the same inputs (the autograd wrapper keeps it alive between forward and backward).
+int corr_backward_tc(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
+                     const CorrParams &p, void *workspace, size_t workspace_bytes, int have_split, cudaStream_t st) {
+    const size_t need = corr_tc_workspace_bytes(p);
+    if (need == 0) return fail(FN2B200_EUNSUPPORTED, "correlation_backward(tc): configuration not supported");
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 127))
+        return fail(FN2B200_EINVAL, "correlation_backward(tc): 128-byte-aligned workspace of %zu bytes required", need);
+    const size_t per = (size_t)p.B * p.C * p.H * p.W;
+    __nv_bfloat16 *w = static_cast<__nv_bfloat16 *>(workspace);
+    int rc = 0;
+    if (!have_split && (rc = corr_tc_split(in1, in2, w, p, st))) return rc;
+    if (gin1 && (rc = launch_bwd_tc<1>(w + 2 * per, w + 3 * per, gout, gin1, p, st))) return rc;
+    if (gin2 && (rc = launch_bwd_tc<2>(w, w + per, gout, gin2, p, st))) return rc;
+    return 0;
 }
 
 }  // namespace fn2

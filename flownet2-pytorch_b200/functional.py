@@ -88,10 +88,19 @@ def correlation_backward(input1, input2, grad_output, pad_size, kernel_size, max
     with torch.cuda.device_of(a):
         g1 = (out1 if out1 is not None else torch.empty_like(a)) if need1 else None
         g2 = (out2 if out2 is not None else torch.empty_like(b)) if need2 else None
-        check(LIB.fn2b200_correlation_backward(_ptr(a), _ptr(b), _ptr(g), _ptr(g1), _ptr(g2), B, C, H, W,
-                                               pad_size, kernel_size, max_displacement, stride1, stride2,
-                                               int(corr_multiply), _stream(a)),
-              "correlation_backward")
+        ws_bytes = int(LIB.fn2b200_correlation_backward_workspace(B, C, H, W, pad_size, kernel_size,
+                                                                  max_displacement, stride1, stride2))
+        if ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+            check(LIB.fn2b200_correlation_backward_ws(_ptr(a), _ptr(b), _ptr(g), _ptr(g1), _ptr(g2), B, C, H, W,
+                                                      pad_size, kernel_size, max_displacement, stride1, stride2,
+                                                      int(corr_multiply), _ptr(ws), ws_bytes, 0, _stream(a)),
+                  "correlation_backward")
+        else:
+            check(LIB.fn2b200_correlation_backward(_ptr(a), _ptr(b), _ptr(g), _ptr(g1), _ptr(g2), B, C, H, W,
+                                                   pad_size, kernel_size, max_displacement, stride1, stride2,
+                                                   int(corr_multiply), _stream(a)),
+                  "correlation_backward")
     return g1, g2
 
 

@@ -85,6 +85,19 @@ int fn2b200_correlation_forward_ws(const float *input1, const float *input2, flo
                                    size_t workspace_bytes, void *stream);
 
 /*
+ * Tensor-core backward, same workspace size and layout as the forward's.  workspace_has_split != 0
+ * promises that the workspace still holds what fn2b200_correlation_forward_ws wrote for the SAME
+ * input1/input2 (the split pass is then skipped).  FN2B200_CORR_BWD=fma forces the FMA kernels.
+ */
+size_t fn2b200_correlation_backward_workspace(int B, int C, int H, int W, int pad_size, int kernel_size,
+                                              int max_displacement, int stride1, int stride2);
+int fn2b200_correlation_backward_ws(const float *input1, const float *input2, const float *grad_output,
+                                    float *grad_input1, float *grad_input2, int B, int C, int H, int W,
+                                    int pad_size, int kernel_size, int max_displacement, int stride1,
+                                    int stride2, int corr_type_multiply, void *workspace,
+                                    size_t workspace_bytes, int workspace_has_split, void *stream);
+
+/*
  * grad_output: [B,D,oH,oW]; grad_input1, grad_input2: [B,C,H,W] (either may be NULL to skip it).
  * stride1 must be 1 (the reference's backward indexes out of bounds otherwise,
  * correlation_cuda_kernel.cu:163-164 vs :520) -> FN2B200_EUNSUPPORTED.

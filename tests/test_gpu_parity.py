@@ -83,6 +83,15 @@ def test_correlation_tc_matches_fma_path(monkeypatch):
     assert f._lib.LIB.fn2b200_correlation_path(256, 24, 40, 20, 1, 20, 1, 2) == 2
     e = rel_err(out_tc.cpu().numpy(), out_fma.cpu().numpy())
     assert 0 < e < 5e-5, e          # different arithmetic (not bit-identical), far inside 1e-4
+    go = _randn(tuple(out_fma.shape), 52).cuda()
+    g1_tc, g2_tc = f.functional.correlation_backward(a, b, go, 20, 1, 20, 1, 2)
+    monkeypatch.setenv("FN2B200_CORR_BWD", "fma")
+    g1_fma, g2_fma = f.functional.correlation_backward(a, b, go, 20, 1, 20, 1, 2)
+    monkeypatch.delenv("FN2B200_CORR_BWD")
+    e1, e2 = rel_err(g1_tc.cpu().numpy(), g1_fma.cpu().numpy()), rel_err(g2_tc.cpu().numpy(), g2_fma.cpu().numpy())
+    assert 0 < e1 < 5e-5 and 0 < e2 < 5e-5, (e1, e2)
+    only1, none2 = f.functional.correlation_backward(a, b, go, 20, 1, 20, 1, 2, need2=False)
+    assert none2 is None and rel_err(only1.cpu().numpy(), g1_fma.cpu().numpy()) < 5e-5
     # badly scaled inputs: the hi/lo split must not lose the small operand
     out_tc = f.functional.correlation_forward(a * 1e-3, b * 3e4, 20, 1, 20, 1, 2)
     assert rel_err(out_tc.cpu().numpy(), (out_fma * 30.0).cpu().numpy()) < 5e-5
