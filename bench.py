@@ -264,11 +264,13 @@ def build_impl(impl, dev):
         import flownet2_b200
         F2 = flownet2_b200.functional
 
+        state = {"ws": None}     # forward -> backward workspace hand-over, as the autograd Function does
+
         def fwd(a, b, out):
-            F2.correlation_forward(a, b, *prm, 1, out=out)
+            _, state["ws"] = F2.correlation_forward(a, b, *prm, 1, out=out, return_workspace=True)
 
         def bwd(a, b, go, g1, g2):
-            F2.correlation_backward(a, b, go, *prm, 1, out1=g1, out2=g2)
+            F2.correlation_backward(a, b, go, *prm, 1, out1=g1, out2=g2, workspace=state["ws"])
         return "ours", fwd, bwd, F2.launch_count
     from oracle import ref as oref
     ext = oref.load_extension("correlation_cuda")

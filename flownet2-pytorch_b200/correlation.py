@@ -24,8 +24,12 @@ class CorrelationFunction(Function):
         ctx.stride1 = stride1
         ctx.stride2 = stride2
         ctx.corr_multiply = corr_multiply
-        out = F2.correlation_forward(input1, input2, pad_size, kernel_size, max_displacement, stride1, stride2,
-                                     corr_multiply)
+        keep = torch.is_grad_enabled() and (input1.requires_grad or input2.requires_grad)
+        out, ws = F2.correlation_forward(input1, input2, pad_size, kernel_size, max_displacement, stride1, stride2,
+                                         corr_multiply, return_workspace=True)
+        # tensor-core path: keep the bf16 hi/lo copies of the inputs for backward (the reference keeps
+        # nothing but recomputes its padded copies, correlation_cuda_kernel.cu:495-517); freed with ctx
+        ctx.workspace = ws if keep else None
         return out if input1.dtype == torch.float32 else out.to(input1.dtype)
 
     @staticmethod
@@ -35,7 +39,8 @@ class CorrelationFunction(Function):
         need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g1, g2 = F2.correlation_backward(input1, input2, grad_output, ctx.pad_size, ctx.kernel_size,
                                          ctx.max_displacement, ctx.stride1, ctx.stride2, ctx.corr_multiply,
-                                         need1=need1, need2=need2)
+                                         need1=need1, need2=need2, workspace=getattr(ctx, "workspace", None))
+        ctx.workspace = None
         if g1 is not None and g1.dtype != input1.dtype:
             g1 = g1.to(input1.dtype)
         if g2 is not None and g2.dtype != input2.dtype:

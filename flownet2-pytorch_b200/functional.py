@@ -44,8 +44,22 @@ def correlation_out_shape(C, H, W, pad_size, kernel_size, max_displacement, stri
     return D.value, oH.value, oW.value
 
 
+class CorrWorkspace(object):
+    """Scratch of the tensor-core correlation path (bf16 hi/lo copies of input1/input2).  Returned by
+    ``correlation_forward(..., return_workspace=True)`` and accepted by ``correlation_backward`` so the
+    backward can skip the split pass when it runs on the SAME inputs (what autograd does)."""
+    __slots__ = ("buf", "key")
+
+    def __init__(self, buf, key):
+        self.buf, self.key = buf, key
+
+
+def _ws_key(a, b, prm):
+    return (a.data_ptr(), b.data_ptr(), a._version, b._version, tuple(a.shape)) + tuple(prm)
+
+
 def correlation_forward(input1, input2, pad_size, kernel_size, max_displacement, stride1, stride2,
-                        corr_multiply=1, out=None):
+                        corr_multiply=1, out=None, return_workspace=False):
     _require_cuda(input1, input2)
     if input1.dim() != 4 or input1.shape != input2.shape:
         raise ValueError("correlation: input1/input2 must be 4-D with equal shapes, got %s and %s"
@@ -69,15 +83,17 @@ def correlation_forward(input1, input2, pad_size, kernel_size, max_displacement,
                                                      max_displacement, stride1, stride2, int(corr_multiply),
                                                      _ptr(ws), ws_bytes, _stream(a)),
                   "correlation_forward")
+            wsobj = CorrWorkspace(ws, _ws_key(a, b, (pad_size, kernel_size, max_displacement, stride1, stride2)))
         else:
             check(LIB.fn2b200_correlation_forward(_ptr(a), _ptr(b), _ptr(out), B, C, H, W, pad_size, kernel_size,
                                                   max_displacement, stride1, stride2, int(corr_multiply), _stream(a)),
                   "correlation_forward")
-    return out
+            wsobj = None
+    return (out, wsobj) if return_workspace else out
 
 
 def correlation_backward(input1, input2, grad_output, pad_size, kernel_size, max_displacement, stride1,
-                         stride2, corr_multiply=1, need1=True, need2=True, out1=None, out2=None):
+                         stride2, corr_multiply=1, need1=True, need2=True, out1=None, out2=None, workspace=None):
     _require_cuda(input1, input2, grad_output)
     a, b, g = _f32c(input1), _f32c(input2), _f32c(grad_output)
     B, C, H, W = a.shape
@@ -91,10 +107,12 @@ def correlation_backward(input1, input2, grad_output, pad_size, kernel_size, max
         ws_bytes = int(LIB.fn2b200_correlation_backward_workspace(B, C, H, W, pad_size, kernel_size,
                                                                   max_displacement, stride1, stride2))
         if ws_bytes:
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+            have = int(workspace is not None and workspace.buf.numel() >= ws_bytes and workspace.buf.device == a.device
+                       and workspace.key == _ws_key(a, b, (pad_size, kernel_size, max_displacement, stride1, stride2)))
+            ws = workspace.buf if have else torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
             check(LIB.fn2b200_correlation_backward_ws(_ptr(a), _ptr(b), _ptr(g), _ptr(g1), _ptr(g2), B, C, H, W,
                                                       pad_size, kernel_size, max_displacement, stride1, stride2,
-                                                      int(corr_multiply), _ptr(ws), ws_bytes, 0, _stream(a)),
+                                                      int(corr_multiply), _ptr(ws), ws_bytes, have, _stream(a)),
                   "correlation_backward")
         else:
             check(LIB.fn2b200_correlation_backward(_ptr(a), _ptr(b), _ptr(g), _ptr(g1), _ptr(g2), B, C, H, W,

@@ -140,6 +140,30 @@ def test_correlation_autograd_module_and_noncontiguous():
     assert_close(a2.grad.cpu().numpy(), r1, TOL, "autograd gI1 only")
 
 
+def test_correlation_autograd_tensor_core_path_reuses_workspace():
+    """C % 64 == 0 -> tensor-core forward AND backward through the autograd Function; the backward
+    reuses the forward's hi/lo workspace; a second backward-capable call after an in-place input
+    update must not reuse stale copies."""
+    f = _f2()
+    a0, b0 = _randn((1, 64, 12, 20), 60), _randn((1, 64, 12, 20), 61)
+    a, b = a0.cuda().requires_grad_(), b0.cuda().requires_grad_()
+    out = f.Correlation(20, 1, 20, 1, 2, 1)(a, b)
+    go = _randn(tuple(out.shape), 62)
+    out.backward(go.cuda())
+    r1, r2 = orc.correlation_backward(a0.numpy(), b0.numpy(), go.numpy(), 20, 1, 20, 1, 2)
+    assert_close(a.grad.cpu().numpy(), r1, TOL, "tc autograd gI1")
+    assert_close(b.grad.cpu().numpy(), r2, TOL, "tc autograd gI2")
+    # functional API: stale workspace (input modified in place after the forward) is detected
+    x, y = a0.cuda(), b0.cuda()
+    _, ws = f.functional.correlation_forward(x, y, 20, 1, 20, 1, 2, return_workspace=True)
+    assert ws is not None
+    y.mul_(2.0)
+    g1, _ = f.functional.correlation_backward(x, y, go.cuda(), 20, 1, 20, 1, 2, workspace=ws)
+    assert_close(g1.cpu().numpy(), 2.0 * r1, TOL, "stale workspace must be ignored")
+    with torch.no_grad():
+        assert f.Correlation(20, 1, 20, 1, 2, 1)(x, y).shape == out.shape
+
+
 def test_correlation_side_stream():
     f = _f2()
     a, b = _randn((1, 32, 16, 64), 8).cuda(), _randn((1, 32, 16, 64), 9).cuda()
