@@ -23,6 +23,7 @@
 //                    scale by 1/C and store to out[n][(tj,ti)][y][x]
 #include "umma.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace fn2 {
 
@@ -34,17 +35,18 @@ constexpr int TC_NU = TC_HH / TC_UR;           // 7 units per tile
 constexpr int TC_N = TC_UR * TC_HW;            // 144 accumulator columns per unit
 constexpr int TC_KB = 64;                      // channels per k-block (128 B of bf16)
 constexpr int TC_MAXKB = 4;                    // C <= 256
-constexpr int TC_BST = 2;                      // B ring stages
+constexpr int TC_MAXBST = 6;                   // B ring stages: as many as shared memory allows (runtime)
 constexpr int TC_NACC = 3;                     // TMEM accumulator buffers
 constexpr int TC_DS = 2 * TC_DR + 1;           // 21
 constexpr int TC_ABLK = 128 * 128;             // bytes of one A k-block (128 rows x 128 B)
 constexpr int TC_BBLK = TC_N * 128;            // bytes of one B k-block (144 rows x 128 B)
 constexpr int TC_EPITCH = TC_HW + 1;           // 37 floats per epilogue staging row
-constexpr int TC_SMEM_A = 2 * TC_MAXKB * TC_ABLK;          // 131072
-constexpr int TC_SMEM_B = TC_BST * 2 * TC_BBLK;            // 73728
 constexpr int TC_SMEM_E = 128 * TC_EPITCH * 4;             // 18944
-constexpr int TC_NBAR = 2 * TC_MAXKB + 2 * TC_BST + 2 * TC_NACC;
-constexpr int TC_SMEM = TC_SMEM_A + TC_SMEM_B + TC_SMEM_E + TC_NBAR * 8 + 16 + 1024;
+constexpr int TC_NBAR = 2 * TC_MAXKB + 2 * TC_MAXBST + 2 * TC_NACC;
+constexpr int TC_SMEM_MAX = 232448;                        // 227 KB opt-in limit per CTA
+__host__ __device__ constexpr int tc_smem_bytes(int nkb, int bst) {
+    return 2 * nkb * TC_ABLK + bst * 2 * TC_BBLK + TC_SMEM_E + TC_NBAR * 8 + 16 + 1024;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Prepass: NCHW fp32 -> parity-class-separated NHWC bf16 hi / lo
@@ -119,28 +121,27 @@ __device__ __forceinline__ TcTile tc_decode(int t, int nxt, int nyt) {
 __global__ void __launch_bounds__(192, 1)
 corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ CUtensorMap m1l,
                    const __grid_constant__ CUtensorMap m2h, const __grid_constant__ CUtensorMap m2l,
-                   float *__restrict__ out, int B, int C, int H, int W, int ntiles) {
+                   float *__restrict__ out, int B, int C, int H, int W, int ntiles, int TC_BST, int hint) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char *sA = smem;                                   // [hl][kb][128 x 128 B]
-    unsigned char *sB = smem + TC_SMEM_A;                       // [stage][hl][144 x 128 B]
-    float *sE = reinterpret_cast<float *>(sB + TC_SMEM_B);      // [128][37]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(sE) + TC_SMEM_E);
-    uint64_t *a_full = bars, *a_empty = bars + TC_MAXKB;
-    uint64_t *b_full = bars + 2 * TC_MAXKB, *b_empty = b_full + TC_BST;
-    uint64_t *acc_full = b_empty + TC_BST, *acc_empty = acc_full + TC_NACC;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + TC_NBAR);
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Hc = H >> 1, Wc = W >> 1;
     const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
     const int nkb = C / TC_KB;
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sA = smem;                                   // [hl][kb][128 x 128 B]
+    unsigned char *sB = smem + 2 * nkb * TC_ABLK;               // [stage][hl][144 x 128 B]
+    float *sE = reinterpret_cast<float *>(sB + TC_BST * 2 * TC_BBLK);   // [128][37]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(sE) + TC_SMEM_E);
+    uint64_t *a_full = bars, *a_empty = bars + TC_MAXKB;
+    uint64_t *b_full = bars + 2 * TC_MAXKB, *b_empty = b_full + TC_MAXBST;
+    uint64_t *acc_full = b_empty + TC_MAXBST, *acc_empty = acc_full + TC_NACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + TC_NBAR);
 
     if (tid == 0) {
         prefetch_tensormap(&m1h); prefetch_tensormap(&m1l);
         prefetch_tensormap(&m2h); prefetch_tensormap(&m2l);
         for (int i = 0; i < TC_MAXKB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < TC_BST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < TC_MAXBST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < TC_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_barrier_init();
     }
@@ -155,23 +156,28 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
         if (lane == 0) {
             uint32_t bcount = 0;
             int it = 0;
+            const uint64_t pol = l2_policy_evict_last();
+            auto load = [&](void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3) {
+                if (hint) tma_load_4d_hint(dst, m, bar, c0, c1, c2, c3, pol);
+                else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+            };
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
                 const TcTile T = tc_decode(t, nxt, nyt);
                 const int img = T.n * 4 + T.py * 2 + T.px;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&a_empty[kb], (it & 1) ^ 1);
                     mbar_arrive_expect_tx(&a_full[kb], 2 * TC_ABLK);
-                    tma_load_4d(sA + (0 * TC_MAXKB + kb) * TC_ABLK, &m1h, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
-                    tma_load_4d(sA + (1 * TC_MAXKB + kb) * TC_ABLK, &m1l, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
+                    load(sA + (0 * nkb + kb) * TC_ABLK, &m1h, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
+                    load(sA + (1 * nkb + kb) * TC_ABLK, &m1l, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
                 }
                 for (int u = 0; u < TC_NU; ++u)
                     for (int kb = 0; kb < nkb; ++kb, ++bcount) {
                         const int s = bcount % TC_BST;
                         mbar_wait(&b_empty[s], ((bcount / TC_BST) & 1) ^ 1);
                         mbar_arrive_expect_tx(&b_full[s], 2 * TC_BBLK);
-                        tma_load_4d(sB + (s * 2 + 0) * TC_BBLK, &m2h, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
+                        load(sB + (s * 2 + 0) * TC_BBLK, &m2h, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
                                     T.yc0 - TC_DR + u * TC_UR, img);
-                        tma_load_4d(sB + (s * 2 + 1) * TC_BBLK, &m2l, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
+                        load(sB + (s * 2 + 1) * TC_BBLK, &m2l, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
                                     T.yc0 - TC_DR + u * TC_UR, img);
                     }
             }
@@ -193,8 +199,8 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
                         const int s = bcount % TC_BST;
                         mbar_wait(&b_full[s], (bcount / TC_BST) & 1);
                         tcgen05_fence_after();
-                        const uint64_t ah = umma_desc_k_sw128(smem_u32(sA + (0 * TC_MAXKB + kb) * TC_ABLK));
-                        const uint64_t al = umma_desc_k_sw128(smem_u32(sA + (1 * TC_MAXKB + kb) * TC_ABLK));
+                        const uint64_t ah = umma_desc_k_sw128(smem_u32(sA + (0 * nkb + kb) * TC_ABLK));
+                        const uint64_t al = umma_desc_k_sw128(smem_u32(sA + (1 * nkb + kb) * TC_ABLK));
                         const uint64_t bh = umma_desc_k_sw128(smem_u32(sB + (s * 2 + 0) * TC_BBLK));
                         const uint64_t bl = umma_desc_k_sw128(smem_u32(sB + (s * 2 + 1) * TC_BBLK));
 #pragma unroll
@@ -243,7 +249,7 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
                         float *o = obase + (long)(tj * TC_DS) * plane;
                         const float *rp = row + px_t;
 #pragma unroll
-                        for (int ti = 0; ti < TC_DS; ++ti) o[ti * plane] = rp[ti] / nelems;
+                        for (int ti = 0; ti < TC_DS; ++ti) __stcs(o + ti * plane, rp[ti] / nelems);
                     }
                 }
                 tcgen05_fence_before();
@@ -273,25 +279,26 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 constexpr int TB_KS = TC_N / 16;                   // 9 k-steps per unit
 constexpr int TB_AHL = TB_KS * 4096;               // 36864 B: one of {hi, lo} of a unit's A
 constexpr int TB_ASTG = 2 * TB_AHL;                // 73728 B per A stage
-constexpr int TB_NAST = 2, TB_NBST = 2, TB_NACC = 2;
+constexpr int TB_NAST = 2, TB_MAXBST = 4, TB_NACC = 2;
 constexpr int TB_SMEM_A = TB_NAST * TB_ASTG;       // 147456
-constexpr int TB_SMEM_B = TB_NBST * 2 * TC_BBLK;   // 73728
-constexpr int TB_NBAR = 2 * TB_NAST + 2 * TB_NBST + 2 * TB_NACC;
-constexpr int TB_SMEM = TB_SMEM_A + TB_SMEM_B + TB_NBAR * 8 + 16 + 1024;
+constexpr int TB_NBAR = 2 * TB_NAST + 2 * TB_MAXBST + 2 * TB_NACC;
+__host__ __device__ constexpr int tb_smem_bytes(int bst) {
+    return TB_SMEM_A + bst * 2 * TC_BBLK + TB_NBAR * 8 + 16 + 1024;
+}
 
 template <int WHICH>
 __global__ void __launch_bounds__(320, 1)
 corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constant__ CUtensorMap mol,
                    const float *__restrict__ gout, float *__restrict__ gin, int B, int C, int H, int W,
-                   int ntiles) {
+                   int ntiles, int TB_NBST, int hint) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sA = smem;                          // [stage][hl][9 k-steps][2 chunks][16 groups][8 x 16 B]
     unsigned char *sB = smem + TB_SMEM_A;              // [stage][hl][144 rows x 128 B] (SW128)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TB_SMEM_B);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TB_NBST * 2 * TC_BBLK);
     uint64_t *a_full = bars, *a_empty = a_full + TB_NAST;
-    uint64_t *b_full = a_empty + TB_NAST, *b_empty = b_full + TB_NBST;
-    uint64_t *acc_full = b_empty + TB_NBST, *acc_empty = acc_full + TB_NACC;
+    uint64_t *b_full = a_empty + TB_NAST, *b_empty = b_full + TB_MAXBST;
+    uint64_t *acc_full = b_empty + TB_MAXBST, *acc_empty = acc_full + TB_NACC;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + TB_NBAR);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -303,7 +310,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
     if (tid == 0) {
         prefetch_tensormap(&moh); prefetch_tensormap(&mol);
         for (int i = 0; i < TB_NAST; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < TB_NBST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < TB_MAXBST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < TB_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_barrier_init();
     }
@@ -317,6 +324,11 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
         // ===================== TMA producer: the other input's halo chunks =====================
         if (lane == 0) {
             uint32_t bcount = 0;
+            const uint64_t pol = l2_policy_evict_last();
+            auto load = [&](void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3) {
+                if (hint) tma_load_4d_hint(dst, m, bar, c0, c1, c2, c3, pol);
+                else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+            };
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 const TcTile T = tc_decode(t, nxt, nyt);
                 const int img = T.n * 4 + T.py * 2 + T.px;
@@ -325,9 +337,9 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                         const int s = bcount % TB_NBST;
                         mbar_wait(&b_empty[s], ((bcount / TB_NBST) & 1) ^ 1);
                         mbar_arrive_expect_tx(&b_full[s], 2 * TC_BBLK);
-                        tma_load_4d(sB + (s * 2 + 0) * TC_BBLK, &moh, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
+                        load(sB + (s * 2 + 0) * TC_BBLK, &moh, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
                                     T.yc0 - TC_DR + u * TC_UR, img);
-                        tma_load_4d(sB + (s * 2 + 1) * TC_BBLK, &mol, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
+                        load(sB + (s * 2 + 1) * TC_BBLK, &mol, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
                                     T.yc0 - TC_DR + u * TC_UR, img);
                     }
             }
@@ -453,7 +465,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                 tmem_ld_wait();
                 if (pix_ok) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[(long)(c0 + i) * plane] = r[i] / nelems;
+                    for (int i = 0; i < 32; ++i) __stcs(o + (long)(c0 + i) * plane, r[i] / nelems);
                 }
             }
             tcgen05_fence_before();
@@ -468,6 +480,14 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
+// tuning knobs for experiments (read per call, no cached state): FN2B200_TC_BST, FN2B200_TC_HINT
+static int tc_env_int(const char *name, int def, int lo, int hi) {
+    const char *e = getenv(name);
+    if (!e || !*e) return def;
+    int v = atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
 bool corr_tc_supported(const CorrParams &p) {
     return p.k == 1 && p.s1 == 1 && p.s2 == 2 && p.dr == TC_DR && p.pad == p.md && (p.H % 2 == 0) &&
            (p.W % 2 == 0) && (p.C % TC_KB == 0) && p.C <= TC_KB * TC_MAXKB && p.H >= 2 && p.W >= 2;
@@ -521,10 +541,16 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrPa
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    const int nkb = p.C / TC_KB;
+    int bst = 2;
+    while (bst < TC_MAXBST && tc_smem_bytes(nkb, bst + 1) <= TC_SMEM_MAX) ++bst;
+    bst = tc_env_int("FN2B200_TC_BST", bst, 2, bst);
+    const int hint = tc_env_int("FN2B200_TC_HINT", 1, 0, 1);
+    const int smem = tc_smem_bytes(nkb, bst);
+    cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "correlation_forward(tc): smem attribute (%s)", cudaGetErrorString(e));
     const int grid = ntiles < sms ? ntiles : sms;
-    corr_fwd_tc_kernel<<<grid, 192, TC_SMEM, st>>>(m1h, m1l, m2h, m2l, out, p.B, p.C, p.H, p.W, ntiles);
+    corr_fwd_tc_kernel<<<grid, 192, smem, st>>>(m1h, m1l, m2h, m2l, out, p.B, p.C, p.H, p.W, ntiles, bst, hint);
     count_launch();
     return check_launch("correlation_forward(tc)");
 }
@@ -543,10 +569,15 @@ static int launch_bwd_tc(const __nv_bfloat16 *oh, const __nv_bfloat16 *ol, const
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     auto kern = corr_bwd_tc_kernel<WHICH>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
+    int bst = 2;
+    while (bst < TB_MAXBST && tb_smem_bytes(bst + 1) <= TC_SMEM_MAX) ++bst;
+    bst = tc_env_int("FN2B200_TC_BST", bst, 2, bst);
+    const int hint = tc_env_int("FN2B200_TC_HINT", 1, 0, 1);
+    const int smem = tb_smem_bytes(bst);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "correlation_backward(tc): smem attribute (%s)", cudaGetErrorString(e));
     const int grid = ntiles < sms ? ntiles : sms;
-    kern<<<grid, 320, TB_SMEM, st>>>(moh, mol, gout, gin, p.B, p.C, p.H, p.W, ntiles);
+    kern<<<grid, 320, smem, st>>>(moh, mol, gout, gin, p.B, p.C, p.H, p.W, ntiles, bst, hint);
     count_launch();
     return check_launch("correlation_backward(tc)");
 }
