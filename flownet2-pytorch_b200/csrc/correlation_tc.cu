@@ -222,7 +222,10 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
         const int p = quad * 32 + lane;            // tile pixel = TMEM lane = accumulator row
         const int py_t = p >> 4, px_t = p & 15;
         float *row = sE + p * TC_EPITCH;
-        const float nelems = (float)C;
+        // 1/(k*k*C): exact for power-of-two C (FlowNetC: 256) -> bit-identical to the reference's divide;
+        // otherwise within 1 ulp.  (An IEEE divide here costs a slow-path call + reconvergence barrier
+        // per output and serialises the epilogue: measured 13K cycles per unit.)
+        const float inv_nelems = 1.0f / (float)C;
         const long plane = (long)H * W;
         uint32_t acount = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -249,7 +252,7 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
                         float *o = obase + (long)(tj * TC_DS) * plane;
                         const float *rp = row + px_t;
 #pragma unroll
-                        for (int ti = 0; ti < TC_DS; ++ti) __stcs(o + ti * plane, rp[ti] / nelems);
+                        for (int ti = 0; ti < TC_DS; ++ti) __stcs(o + ti * plane, rp[ti] * inv_nelems);
                     }
                 }
                 tcgen05_fence_before();
@@ -395,42 +398,49 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
             for (int u = 0; u < TC_NU; ++u, ++ucount) {
                 const int as = ucount % TB_NAST;
                 mbar_wait(&a_empty[as], ((ucount / TB_NAST) & 1) ^ 1);
-                unsigned char *ah = sA + as * TB_ASTG + row_off, *al = ah + TB_AHL;
+                // (1) issue ALL gradOutput loads of this unit (4 halo rows x 21 displacements) before
+                //     touching shared memory: one DRAM round trip per unit instead of four
+                float v[TC_UR][TC_DS];
 #pragma unroll
-                for (int i = 0; i < 2 * TB_KS; ++i) {           // zero this thread's row (18 x 16 B, hi and lo)
-                    *reinterpret_cast<uint4 *>(ah + i * 2048) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4 *>(al + i * 2048) = make_uint4(0, 0, 0, 0);
-                }
-#pragma unroll 1
                 for (int hrl = 0; hrl < TC_UR; ++hrl) {
                     const int tjp = u * TC_UR + hrl - py_t;       // tj + 10 of this (pixel row, halo row) pair
-                    if (tjp < 0 || tjp >= TC_DS) continue;
+                    bool row_ok = (tjp >= 0) && (tjp < TC_DS);
                     const float *src;
                     long step;
-                    bool row_ok;
-                    int xs0;
+                    int xs0 = 0;
                     if (WHICH == 1) {
-                        row_ok = pix_ok;                          // gO at the output pixel itself
+                        row_ok = row_ok && pix_ok;                // gO at the output pixel itself
                         src = gn + (long)(tjp * TC_DS) * plane + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
                         step = plane;                             // next ti -> next plane
-                        xs0 = 0;
                     } else {
                         const int ycs = T.yc0 - TC_DR + u * TC_UR + hrl;   // source pixel row (class coords)
-                        row_ok = (ycs >= 0) && (ycs < Hc);
+                        row_ok = row_ok && (ycs >= 0) && (ycs < Hc);
                         xs0 = T.xc0 - TC_DR + px_t;                        // source column for j = 0
                         // plane (20 - tjp, 20 - j), pixel (ycs, xs0 + j): j -> j+1 moves -1 plane, +2 in x
                         src = gn + (long)((TC_DS - 1 - tjp) * TC_DS + (TC_DS - 1)) * plane +
                               (long)(2 * ycs + T.py) * W + (2 * xs0 + T.px);
                         step = 2 - plane;
                     }
-                    if (!row_ok) continue;
 #pragma unroll
                     for (int j = 0; j < TC_DS; ++j) {
-                        float v;
-                        if (WHICH == 1) v = __ldg(src + j * step);
-                        else v = (xs0 + j >= 0 && xs0 + j < Wc) ? __ldg(src + j * step) : 0.f;
-                        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-                        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+                        const bool ok = row_ok && (WHICH == 1 || (xs0 + j >= 0 && xs0 + j < Wc));
+                        v[hrl][j] = ok ? __ldg(src + j * step) : 0.f;
+                    }
+                }
+                // (2) zero this thread's row (18 x 16 B, hi and lo), then scatter the band entries
+                unsigned char *ah = sA + as * TB_ASTG + row_off, *al = ah + TB_AHL;
+#pragma unroll
+                for (int i = 0; i < 2 * TB_KS; ++i) {
+                    *reinterpret_cast<uint4 *>(ah + i * 2048) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(al + i * 2048) = make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int hrl = 0; hrl < TC_UR; ++hrl) {
+#pragma unroll
+                    for (int j = 0; j < TC_DS; ++j) {
+                        const float x = v[hrl][j];
+                        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                        const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
                         const int k = hrl * TC_HW + px_t + j;
                         const uint32_t off = (k >> 4) * 4096 + ((k >> 3) & 1) * 2048 + (k & 7) * 2;
                         *reinterpret_cast<unsigned short *>(ah + off) = __bfloat16_as_ushort(h);
@@ -446,7 +456,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
         const int quad = warp & 3;
         const int p = quad * 32 + lane;
         const int py_t = p >> 4, px_t = p & 15;
-        const float nelems = (float)C;
+        const float inv_nelems = 1.0f / (float)C;
         uint32_t tcount = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
             const TcTile T = tc_decode(t, nxt, nyt);
@@ -465,7 +475,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                 tmem_ld_wait();
                 if (pix_ok) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) __stcs(o + (long)(c0 + i) * plane, r[i] / nelems);
+                    for (int i = 0; i < 32; ++i) __stcs(o + (long)(c0 + i) * plane, r[i] * inv_nelems);
                 }
             }
             tcgen05_fence_before();

@@ -30,8 +30,8 @@ for C in (256, 128, 64):
     go = torch.randn(8, 441, 112, 256, device=dev, generator=g)
     out = torch.empty(8, 441, 112, 256, device=dev)
     g1, g2 = torch.empty_like(a), torch.empty_like(b)
-    for hint in (1, 0):
-        for bst in (2, 3, 4):
+    for hint in (1,):
+        for bst in (4,):
             os.environ["FN2B200_TC_BST"] = str(bst)
             os.environ["FN2B200_TC_HINT"] = str(hint)
             _, ws = F2.correlation_forward(a, b, 20, 1, 20, 1, 2, out=out, return_workspace=True)
