@@ -113,7 +113,7 @@ int make_tensor_map_bf16_sw128(CUtensorMap *map, const void *base, int rank, con
 }
 
 int umma_selftest(const void *A, const void *B, float *D, int K, cudaStream_t st);
-int umma_selftest2(const void *A, const void *Bt, float *D, cudaStream_t st);
+int umma_selftest2(const void *A, const void *Bt, float *D, int a_sw32, cudaStream_t st);
 
 static int fill_corr_params(CorrParams &p, int B, int C, int H, int W, int pad, int k, int md,
                             int s1, int s2) {
@@ -163,7 +163,7 @@ int fn2b200_version(void) { return FN2B200_VERSION; }
 int fn2b200_debug_umma_gemm(const void *A_bf16, const void *B_bf16, float *D, int K, void *stream) {
     if (!A_bf16 || !B_bf16 || !D) return fail(FN2B200_ENULL, "debug_umma_gemm: null pointer");
     if (int rc = bind_device_of(D)) return rc;
-    if (K == -144) return umma_selftest2(A_bf16, B_bf16, D, (cudaStream_t)stream);
+    if (K == -144 || K == -145) return umma_selftest2(A_bf16, B_bf16, D, K == -145, (cudaStream_t)stream);
     return umma_selftest(A_bf16, B_bf16, D, K, (cudaStream_t)stream);
 }
 const char *fn2b200_last_error(void) { return g_err; }

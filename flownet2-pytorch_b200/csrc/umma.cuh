@@ -32,6 +32,21 @@ __device__ __forceinline__ uint64_t umma_desc_k_noswz(uint32_t smem_addr, uint32
     d |= (uint64_t)1 << 46;
     return d;
 }
+// K-major operand, 32-byte swizzle: rows of 32 B (= one K=16 bf16 step), 8-row atoms of 256 B
+// (SBO = 256), 16-byte chunk index XORed with bit 7 of the byte address (row >> 2).  layout type 6.
+__device__ __forceinline__ uint64_t umma_desc_k_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
+// byte offset of element (row r, k in [0,16)) inside one [128 rows x 32 B] SW32 k-step block
+__host__ __device__ constexpr uint32_t sw32_offset(uint32_t r, uint32_t k) {
+    return r * 32u + ((((k >> 3) & 1u) ^ ((r >> 2) & 1u)) << 4) + (k & 7u) * 2u;
+}
 // MN-major operand, 128-byte swizzle: rows are K (128 B = 64 contiguous MN elements each); 8-row
 // groups are SBO = 1024 B apart, successive 64-element MN blocks LBO bytes apart.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {

@@ -96,7 +96,7 @@ constexpr int ST2_K = 144, ST2_N = 64;
 
 __global__ void __launch_bounds__(128, 1)
 umma_selftest2_kernel(const __nv_bfloat16_raw *__restrict__ A, const __grid_constant__ CUtensorMap mapB,
-                      float *__restrict__ D) {
+                      float *__restrict__ D, int a_sw32) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sB = smem;                              // [144 rows(K)][128 B], SW128 (MN-major)
@@ -116,7 +116,9 @@ umma_selftest2_kernel(const __nv_bfloat16_raw *__restrict__ A, const __grid_cons
         const unsigned short *arow = reinterpret_cast<const unsigned short *>(A) + (size_t)p * ST2_K;
         for (int k = 0; k < ST2_K; ++k) {
             const int ks = k >> 4, c = (k >> 3) & 1, e = k & 7;
-            *reinterpret_cast<unsigned short *>(sA + ks * 4096 + c * 2048 + (p >> 3) * 128 + (p & 7) * 16 + e * 2) = arow[k];
+            const uint32_t off = a_sw32 ? ks * 4096 + sw32_offset(p, k & 15)
+                                        : ks * 4096 + c * 2048 + (p >> 3) * 128 + (p & 7) * 16 + e * 2;
+            *reinterpret_cast<unsigned short *>(sA + off) = arow[k];
         }
     }
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -133,7 +135,8 @@ umma_selftest2_kernel(const __nv_bfloat16_raw *__restrict__ A, const __grid_cons
         const uint64_t db = umma_desc_mn_sw128(smem_u32(sB), ST2_K * 128);
 #pragma unroll
         for (int ks = 0; ks < ST2_K / 16; ++ks) {
-            const uint64_t da = umma_desc_k_noswz(smem_u32(sA + ks * 4096), 2048, 128);
+            const uint64_t da = a_sw32 ? umma_desc_k_sw32(smem_u32(sA + ks * 4096))
+                                       : umma_desc_k_noswz(smem_u32(sA + ks * 4096), 2048, 128);
             umma_bf16_ss(tmem_base, da, db + (uint64_t)((ks * 16 * 128) >> 4), idesc, ks != 0);
         }
         umma_commit(&bars[1]);
@@ -153,7 +156,7 @@ umma_selftest2_kernel(const __nv_bfloat16_raw *__restrict__ A, const __grid_cons
     if (warp == 0) tmem_dealloc<64>(tmem_base);
 }
 
-int umma_selftest2(const void *A, const void *Bt, float *D, cudaStream_t st) {
+int umma_selftest2(const void *A, const void *Bt, float *D, int a_sw32, cudaStream_t st) {
     CUtensorMap mb;
     uint64_t dims[2] = {ST2_N, ST2_K};
     uint64_t str[1] = {ST2_N * 2};
@@ -163,7 +166,7 @@ int umma_selftest2(const void *A, const void *Bt, float *D, cudaStream_t st) {
     const int smem = ST2_K * 128 + 9 * 4096 + 1024 + 64;
     cudaError_t e = cudaFuncSetAttribute(umma_selftest2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "umma_selftest2: smem attribute (%s)", cudaGetErrorString(e));
-    umma_selftest2_kernel<<<1, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16_raw *>(A), mb, D);
+    umma_selftest2_kernel<<<1, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16_raw *>(A), mb, D, a_sw32);
     count_launch();
     return check_launch("umma_selftest2");
 }

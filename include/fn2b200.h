@@ -154,7 +154,8 @@ int fn2b200_correlation_path(int C, int H, int W, int pad_size, int kernel_size,
  * device buffers, K a multiple of 64.  K == -144 selects the second form (the backward kernel's
  * operand layouts): D[128 x 64] = A[128 x 144] * Bt[144 x 64], A written to shared memory by the
  * threads in the no-swizzle core-matrix layout, Bt ([K][N] row-major) loaded as an MN-major
- * SW128 operand.  Test hook only (tests/test_gpu_umma.py).
+ * SW128 operand; K == -145 is the same with A in the 32-byte-swizzle K-major layout.
+ * Test hook only (tests/test_gpu_umma.py).
  */
 int fn2b200_debug_umma_gemm(const void *A_bf16, const void *B_bf16, float *D, int K, void *stream);
 

@@ -25,7 +25,8 @@ def test_umma_gemm_matches_cpu(K):
     assert err < 1e-5, err
 
 
-def test_umma_gemm_noswizzle_a_mnmajor_b():
+@pytest.mark.parametrize("mode", [-144, -145])
+def test_umma_gemm_noswizzle_a_mnmajor_b(mode):
     """Operand forms of the tensor-core backward: A built by threads (K-major, no swizzle),
     B^T = [K][N] row-major consumed as an MN-major SW128 operand."""
     from flownet2_b200._lib import LIB, check
@@ -36,7 +37,7 @@ def test_umma_gemm_noswizzle_a_mnmajor_b():
     D = torch.full((128, 64), float("nan"), device="cuda")
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     check(LIB.fn2b200_debug_umma_gemm(ctypes.c_void_p(Ad.data_ptr()), ctypes.c_void_p(Bd.data_ptr()),
-                                      ctypes.c_void_p(D.data_ptr()), -144, st), "debug_umma_gemm(2)")
+                                      ctypes.c_void_p(D.data_ptr()), mode, st), "debug_umma_gemm(2)")
     torch.cuda.synchronize()
     ref = A.double() @ Bt.double()
     err = (D.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
