@@ -273,7 +273,8 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 // per parity class: D[128 tile px][C] += A[128][144] * B[144 halo px][C] over the 7 halo-row units,
 // accumulated in ONE TMEM buffer per tile (C <= 256 fp32 columns, double-buffered across tiles).
 //   A = the banded gradOutput matrix, built per unit by 4 "builder" warps straight from the fp32
-//       gradOutput planes (bf16 hi/lo split on the fly) into the no-swizzle K-major core-matrix layout;
+//       gradOutput planes (bf16 hi/lo split on the fly) into the K-major 32-byte-swizzle layout (the
+//       no-swizzle layout made the 2-byte band scatter 4-way bank conflicted: 70 % of wavefronts);
 //   B = the other input's halo chunk from the prepass copy ([pixel][channel] bf16 = MN-major operand),
 //       one 64-channel block per TMA stage;
 //   3 MMAs (hi*hi, hi*lo, lo*hi) per k-step, N = 64 per instruction.
@@ -370,8 +371,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                         const uint32_t d = tmem_base + ab * 256 + j * TC_KB;
 #pragma unroll
                         for (int ks = 0; ks < TB_KS; ++ks) {
-                            const uint64_t ah = umma_desc_k_noswz(a_hi + ks * 4096, 2048, 128);
-                            const uint64_t al = umma_desc_k_noswz(a_lo + ks * 4096, 2048, 128);
+                            const uint64_t ah = umma_desc_k_sw32(a_hi + ks * 4096);
+                            const uint64_t al = umma_desc_k_sw32(a_lo + ks * 4096);
                             const uint64_t kadv = (uint64_t)((ks * 16 * 128) >> 4);
                             umma_bf16_ss(d, ah, bh + kadv, idesc, (u | ks) != 0);
                             umma_bf16_ss(d, ah, bl + kadv, idesc, 1);
@@ -388,7 +389,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
         // ===================== builders: banded gradOutput matrix A (hi / lo) =====================
         const int p = tid - 64;
         const int py_t = p >> 4, px_t = p & 15;
-        const uint32_t row_off = (p >> 3) * 128 + (p & 7) * 16;
+        const uint32_t row_off = p * 32;                   // SW32 K-major: 32-byte rows, chunk ^= (row >> 2) & 1
+        const uint32_t swz = (p >> 2) & 1;
         uint32_t ucount = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const TcTile T = tc_decode(t, nxt, nyt);
@@ -430,9 +432,11 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                 // (2) zero this thread's row (18 x 16 B, hi and lo), then scatter the band entries
                 unsigned char *ah = sA + as * TB_ASTG + row_off, *al = ah + TB_AHL;
 #pragma unroll
-                for (int i = 0; i < 2 * TB_KS; ++i) {
-                    *reinterpret_cast<uint4 *>(ah + i * 2048) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4 *>(al + i * 2048) = make_uint4(0, 0, 0, 0);
+                for (int ks = 0; ks < TB_KS; ++ks) {
+                    *reinterpret_cast<uint4 *>(ah + ks * 4096) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(ah + ks * 4096 + 16) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(al + ks * 4096) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(al + ks * 4096 + 16) = make_uint4(0, 0, 0, 0);
                 }
 #pragma unroll
                 for (int hrl = 0; hrl < TC_UR; ++hrl) {
@@ -442,7 +446,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                         const __nv_bfloat16 h = __float2bfloat16_rn(x);
                         const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
                         const int k = hrl * TC_HW + px_t + j;
-                        const uint32_t off = (k >> 4) * 4096 + ((k >> 3) & 1) * 2048 + (k & 7) * 2;
+                        const uint32_t off = (k >> 4) * 4096 + ((((k >> 3) & 1) ^ swz) << 4) + (k & 7) * 2;
                         *reinterpret_cast<unsigned short *>(ah + off) = __bfloat16_as_ushort(h);
                         *reinterpret_cast<unsigned short *>(al + off) = __bfloat16_as_ushort(l);
                     }
