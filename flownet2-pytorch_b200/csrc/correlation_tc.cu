@@ -278,7 +278,9 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 //   B = the other input's halo chunk from the prepass copy ([pixel][channel] bf16 = MN-major operand),
 //       one 64-channel block per TMA stage;
 //   3 MMAs (hi*hi, hi*lo, lo*hi) per k-step, N = 64 per instruction.
-// Roles (320 threads): warp 0 TMA, warp 1 MMA, warps 2-5 builders, warps 6-9 epilogue.
+// Roles (448 threads): warp 0 TMA, warp 1 MMA, warps 2-9 builders (two threads per tile pixel, two
+// halo rows each: a single warp per scheduler runs its ~2000 dependent instructions per unit at
+// IPC ~0.2, which made the builder -- not the tensor pipe -- the bottleneck), warps 10-13 epilogue.
 // ------------------------------------------------------------------------------------------------
 constexpr int TB_KS = TC_N / 16;                   // 9 k-steps per unit
 constexpr int TB_AHL = TB_KS * 4096;               // 36864 B: one of {hi, lo} of a unit's A
@@ -286,12 +288,15 @@ constexpr int TB_ASTG = 2 * TB_AHL;                // 73728 B per A stage
 constexpr int TB_NAST = 2, TB_MAXBST = 4, TB_NACC = 2;
 constexpr int TB_SMEM_A = TB_NAST * TB_ASTG;       // 147456
 constexpr int TB_NBAR = 2 * TB_NAST + 2 * TB_MAXBST + 2 * TB_NACC;
+constexpr int TB_NE = TC_UR * TC_DS;               // 84 band entries per (pixel, unit)
+constexpr int TB_OFFTAB = TC_TW * TB_NE * 2;       // 2688 B: uint16 offsets [px_t][hrl*21 + j]
+constexpr int TB_THREADS = 448;                    // warp 0 TMA, 1 MMA, 2-9 builders, 10-13 epilogue
 __host__ __device__ constexpr int tb_smem_bytes(int bst) {
-    return TB_SMEM_A + bst * 2 * TC_BBLK + TB_NBAR * 8 + 16 + 1024;
+    return TB_SMEM_A + bst * 2 * TC_BBLK + TB_OFFTAB + TB_NBAR * 8 + 16 + 1024;
 }
 
 template <int WHICH>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(TB_THREADS, 1)
 corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constant__ CUtensorMap mol,
                    const float *__restrict__ gout, float *__restrict__ gin, int B, int C, int H, int W,
                    int ntiles, int TB_NBST, int hint) {
@@ -299,7 +304,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sA = smem;                          // [stage][hl][9 k-steps][2 chunks][16 groups][8 x 16 B]
     unsigned char *sB = smem + TB_SMEM_A;              // [stage][hl][144 rows x 128 B] (SW128)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TB_NBST * 2 * TC_BBLK);
+    unsigned short *offtab = reinterpret_cast<unsigned short *>(sB + TB_NBST * 2 * TC_BBLK);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TB_NBST * 2 * TC_BBLK + TB_OFFTAB);
     uint64_t *a_full = bars, *a_empty = a_full + TB_NAST;
     uint64_t *b_full = a_empty + TB_NAST, *b_empty = b_full + TB_MAXBST;
     uint64_t *acc_full = b_empty + TB_MAXBST, *acc_empty = acc_full + TB_NACC;
@@ -313,10 +319,17 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
 
     if (tid == 0) {
         prefetch_tensormap(&moh); prefetch_tensormap(&mol);
-        for (int i = 0; i < TB_NAST; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < TB_NAST; ++i) { mbar_init(&a_full[i], 256); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < TB_MAXBST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < TB_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_barrier_init();
+    }
+    // byte offset (without the row term and the swizzle bit) of band entry e = hrl*21 + j of a thread
+    // whose tile column is px: k = hrl*36 + px + j -> (k >> 4) * 4096 + ((k >> 3) & 1) * 16 + (k & 7) * 2
+    for (int i = tid; i < TC_TW * TB_NE; i += TB_THREADS) {
+        const int px = i / TB_NE, e = i % TB_NE;
+        const int k = (e / TC_DS) * TC_HW + px + (e % TC_DS);
+        offtab[i] = (unsigned short)((k >> 4) * 4096 + ((k >> 3) & 1) * 16 + (k & 7) * 2);
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tcgen05_fence_before();
@@ -385,12 +398,14 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                 umma_commit(&acc_full[ab]);
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 10) {
         // ===================== builders: banded gradOutput matrix A (hi / lo) =====================
-        const int p = tid - 64;
+        const int tb = tid - 64;                   // 0..255
+        const int p = tb & 127, half = tb >> 7;    // tile pixel, which two halo rows of each unit
         const int py_t = p >> 4, px_t = p & 15;
-        const uint32_t row_off = p * 32;                   // SW32 K-major: 32-byte rows, chunk ^= (row >> 2) & 1
-        const uint32_t swz = (p >> 2) & 1;
+        const uint32_t row_off = p * 32;           // SW32 K-major: 32-byte rows, chunk ^= (row >> 2) & 1
+        const uint32_t swz16 = ((p >> 2) & 1) << 4;
+        const uint32_t *mytab = reinterpret_cast<const uint32_t *>(offtab + px_t * TB_NE + half * 2 * TC_DS);
         uint32_t ucount = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const TcTile T = tc_decode(t, nxt, nyt);
@@ -399,12 +414,11 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
             const float *gn = gout + (long)T.n * (TC_DS * TC_DS) * plane;
             for (int u = 0; u < TC_NU; ++u, ++ucount) {
                 const int as = ucount % TB_NAST;
-                mbar_wait(&a_empty[as], ((ucount / TB_NAST) & 1) ^ 1);
-                // (1) issue ALL gradOutput loads of this unit (4 halo rows x 21 displacements) before
-                //     touching shared memory: one DRAM round trip per unit instead of four
-                float v[TC_UR][TC_DS];
+                // (1) issue all 42 gradOutput loads of this thread before touching shared memory
+                float v[2][TC_DS];
 #pragma unroll
-                for (int hrl = 0; hrl < TC_UR; ++hrl) {
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int hrl = half * 2 + hh;
                     const int tjp = u * TC_UR + hrl - py_t;       // tj + 10 of this (pixel row, halo row) pair
                     bool row_ok = (tjp >= 0) && (tjp < TC_DS);
                     const float *src;
@@ -426,27 +440,30 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < TC_DS; ++j) {
                         const bool ok = row_ok && (WHICH == 1 || (xs0 + j >= 0 && xs0 + j < Wc));
-                        v[hrl][j] = ok ? __ldg(src + j * step) : 0.f;
+                        v[hh][j] = ok ? __ldg(src + j * step) : 0.f;
                     }
                 }
-                // (2) zero this thread's row (18 x 16 B, hi and lo), then scatter the band entries
+                mbar_wait(&a_empty[as], ((ucount / TB_NAST) & 1) ^ 1);
+                // (2) zero this thread's half of the row: 16-byte chunks [9*half, 9*half + 9) of 18
                 unsigned char *ah = sA + as * TB_ASTG + row_off, *al = ah + TB_AHL;
 #pragma unroll
-                for (int ks = 0; ks < TB_KS; ++ks) {
-                    *reinterpret_cast<uint4 *>(ah + ks * 4096) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4 *>(ah + ks * 4096 + 16) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4 *>(al + ks * 4096) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4 *>(al + ks * 4096 + 16) = make_uint4(0, 0, 0, 0);
+                for (int i = 0; i < 9; ++i) {
+                    const int ch = half * 9 + i;                  // chunk: k-step ch >> 1, 16-byte half ch & 1
+                    const uint32_t zo = (ch >> 1) * 4096 + (((ch & 1) << 4) ^ swz16);   // physical half = logical ^ swizzle
+                    *reinterpret_cast<uint4 *>(ah + zo) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(al + zo) = make_uint4(0, 0, 0, 0);
                 }
+                // (3) scatter the band entries (offsets from the precomputed table)
 #pragma unroll
-                for (int hrl = 0; hrl < TC_UR; ++hrl) {
+                for (int e2 = 0; e2 < TC_DS; ++e2) {              // 21 pairs = 42 entries
+                    const uint32_t two = mytab[e2];
 #pragma unroll
-                    for (int j = 0; j < TC_DS; ++j) {
-                        const float x = v[hrl][j];
+                    for (int q = 0; q < 2; ++q) {
+                        const int e = 2 * e2 + q;                 // hh = e / 21, j = e % 21
+                        const float x = v[e / TC_DS][e % TC_DS];
                         const __nv_bfloat16 h = __float2bfloat16_rn(x);
                         const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-                        const int k = hrl * TC_HW + px_t + j;
-                        const uint32_t off = (k >> 4) * 4096 + ((((k >> 3) & 1) ^ swz) << 4) + (k & 7) * 2;
+                        const uint32_t off = ((two >> (16 * q)) & 0xFFFFu) ^ swz16;
                         *reinterpret_cast<unsigned short *>(ah + off) = __bfloat16_as_ushort(h);
                         *reinterpret_cast<unsigned short *>(al + off) = __bfloat16_as_ushort(l);
                     }
@@ -456,7 +473,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
             }
         }
     } else {
-        // ===================== epilogue (warps 6..9) =====================
+        // ===================== epilogue (warps 10..13) =====================
         const int quad = warp & 3;
         const int p = quad * 32 + lane;
         const int py_t = p >> 4, px_t = p & 15;
@@ -591,7 +608,7 @@ static int launch_bwd_tc(const __nv_bfloat16 *oh, const __nv_bfloat16 *ol, const
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "correlation_backward(tc): smem attribute (%s)", cudaGetErrorString(e));
     const int grid = ntiles < sms ? ntiles : sms;
-    kern<<<grid, 320, smem, st>>>(moh, mol, gout, gin, p.B, p.C, p.H, p.W, ntiles, bst, hint);
+    kern<<<grid, TB_THREADS, smem, st>>>(moh, mol, gout, gin, p.B, p.C, p.H, p.W, ntiles, bst, hint);
     count_launch();
     return check_launch("correlation_backward(tc)");
 }
