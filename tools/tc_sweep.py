@@ -8,6 +8,7 @@ import torch  # noqa: E402
 import flownet2_b200  # noqa: E402
 F2 = flownet2_b200.functional
 dev = torch.device("cuda:0")
+print("torch ok", torch.cuda.get_device_name(0), flush=True)
 
 
 def timeit(fn, n=10):
@@ -35,6 +36,11 @@ for C in (256, 128, 64):
             os.environ["FN2B200_TC_BST"] = str(bst)
             os.environ["FN2B200_TC_HINT"] = str(hint)
             _, ws = F2.correlation_forward(a, b, 20, 1, 20, 1, 2, out=out, return_workspace=True)
+            torch.cuda.synchronize()
+            print("  first fwd done", C, hint, bst, flush=True)
+            F2.correlation_backward(a, b, go, 20, 1, 20, 1, 2, out1=g1, out2=g2, workspace=ws)
+            torch.cuda.synchronize()
+            print("  first bwd done", flush=True)
             tf = timeit(lambda: F2.correlation_forward(a, b, 20, 1, 20, 1, 2, out=out))
             tb = timeit(lambda: F2.correlation_backward(a, b, go, 20, 1, 20, 1, 2, out1=g1, out2=g2, workspace=ws))
             print("C=%3d hint=%d bst<=%d  fwd(incl split) %.3f ms   bwd(2 launches, no split) %.3f ms" % (C, hint, bst, tf, tb), flush=True)
