@@ -414,51 +414,34 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
             const float *gn = gout + (long)T.n * (TC_DS * TC_DS) * plane;
             for (int u = 0; u < TC_NU; ++u, ++ucount) {
                 const int as = ucount % TB_NAST;
-                // (1) issue all 42 gradOutput loads of this thread before touching shared memory, then
-                //     L2-prefetch the same 42 addresses of the NEXT unit (gradOutput streams from DRAM
-                //     exactly once per launch; without the prefetch every unit pays a full DRAM round trip)
+                // (1) issue all 42 gradOutput loads of this thread before touching shared memory
                 float v[2][TC_DS];
-                auto gather = [&](const TcTile &TT, int uu, bool prefetch_only) {
-                    const int ycq = TT.yc0 + py_t, xcq = TT.xc0 + px_t;
-                    const bool okq = (ycq < Hc) && (xcq < Wc);
-                    const float *gnn = gout + (long)TT.n * (TC_DS * TC_DS) * plane;
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int hrl = half * 2 + hh;
-                        const int tjp = uu * TC_UR + hrl - py_t;      // tj + 10 of this (pixel row, halo row) pair
-                        bool row_ok = (tjp >= 0) && (tjp < TC_DS);
-                        const float *src;
-                        long step;
-                        int xs0 = 0;
-                        if (WHICH == 1) {
-                            row_ok = row_ok && okq;                   // gO at the output pixel itself
-                            src = gnn + (long)(tjp * TC_DS) * plane + (long)(2 * ycq + TT.py) * W + (2 * xcq + TT.px);
-                            step = plane;                             // next ti -> next plane
-                        } else {
-                            const int ycs = TT.yc0 - TC_DR + uu * TC_UR + hrl;   // source pixel row (class coords)
-                            row_ok = row_ok && (ycs >= 0) && (ycs < Hc);
-                            xs0 = TT.xc0 - TC_DR + px_t;                         // source column for j = 0
-                            // plane (20 - tjp, 20 - j), pixel (ycs, xs0 + j): j -> j+1 moves -1 plane, +2 in x
-                            src = gnn + (long)((TC_DS - 1 - tjp) * TC_DS + (TC_DS - 1)) * plane +
-                                  (long)(2 * ycs + TT.py) * W + (2 * xs0 + TT.px);
-                            step = 2 - plane;
-                        }
-#pragma unroll
-                        for (int j = 0; j < TC_DS; ++j) {
-                            const bool ok = row_ok && (WHICH == 1 || (xs0 + j >= 0 && xs0 + j < Wc));
-                            if (prefetch_only) {
-                                if (ok) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + j * step));
-                            } else {
-                                v[hh][j] = ok ? __ldg(src + j * step) : 0.f;
-                            }
-                        }
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int hrl = half * 2 + hh;
+                    const int tjp = u * TC_UR + hrl - py_t;       // tj + 10 of this (pixel row, halo row) pair
+                    bool row_ok = (tjp >= 0) && (tjp < TC_DS);
+                    const float *src;
+                    long step;
+                    int xs0 = 0;
+                    if (WHICH == 1) {
+                        row_ok = row_ok && pix_ok;                // gO at the output pixel itself
+                        src = gn + (long)(tjp * TC_DS) * plane + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
+                        step = plane;                             // next ti -> next plane
+                    } else {
+                        const int ycs = T.yc0 - TC_DR + u * TC_UR + hrl;   // source pixel row (class coords)
+                        row_ok = row_ok && (ycs >= 0) && (ycs < Hc);
+                        xs0 = T.xc0 - TC_DR + px_t;                        // source column for j = 0
+                        // plane (20 - tjp, 20 - j), pixel (ycs, xs0 + j): j -> j+1 moves -1 plane, +2 in x
+                        src = gn + (long)((TC_DS - 1 - tjp) * TC_DS + (TC_DS - 1)) * plane +
+                              (long)(2 * ycs + T.py) * W + (2 * xs0 + T.px);
+                        step = 2 - plane;
                     }
-                };
-                gather(T, u, false);
-                if (u + 1 < TC_NU) {
-                    gather(T, u + 1, true);
-                } else if (t + (int)gridDim.x < ntiles) {
-                    gather(tc_decode(t + gridDim.x, nxt, nyt), 0, true);
+#pragma unroll
+                    for (int j = 0; j < TC_DS; ++j) {
+                        const bool ok = row_ok && (WHICH == 1 || (xs0 + j >= 0 && xs0 + j < Wc));
+                        v[hh][j] = ok ? __ldg(src + j * step) : 0.f;
+                    }
                 }
                 mbar_wait(&a_empty[as], ((ucount / TB_NAST) & 1) ^ 1);
                 // (2) zero this thread's half of the row: 16-byte chunks [9*half, 9*half + 9) of 18
