@@ -278,9 +278,10 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 //   B = the other input's halo chunk from the prepass copy ([pixel][channel] bf16 = MN-major operand),
 //       one 64-channel block per TMA stage;
 //   3 MMAs (hi*hi, hi*lo, lo*hi) per k-step, N = 64 per instruction.
-// Roles (448 threads): warp 0 TMA, warp 1 MMA, warps 2-9 builders (two threads per tile pixel, two
-// halo rows each: a single warp per scheduler runs its ~2000 dependent instructions per unit at
-// IPC ~0.2, which made the builder -- not the tensor pipe -- the bottleneck), warps 10-13 epilogue.
+// Roles (704 threads): warp 0 TMA, warp 1 MMA, warps 2-17 builders (FOUR threads per tile pixel, one
+// halo row each -- a single warp per scheduler ran its ~2000 dependent instructions per unit at IPC
+// ~0.2 and made the builder, not the tensor pipe, the bottleneck; each thread now writes its full
+// 36-column segment (zeros outside the band) with 36 packed immediate-offset stores), warps 18-21 epilogue.
 // ------------------------------------------------------------------------------------------------
 constexpr int TB_KS = TC_N / 16;                   // 9 k-steps per unit
 constexpr int TB_AHL = TB_KS * 4096;               // 36864 B: one of {hi, lo} of a unit's A
@@ -288,11 +289,32 @@ constexpr int TB_ASTG = 2 * TB_AHL;                // 73728 B per A stage
 constexpr int TB_NAST = 2, TB_MAXBST = 4, TB_NACC = 2;
 constexpr int TB_SMEM_A = TB_NAST * TB_ASTG;       // 147456
 constexpr int TB_NBAR = 2 * TB_NAST + 2 * TB_MAXBST + 2 * TB_NACC;
-constexpr int TB_NE = TC_UR * TC_DS;               // 84 band entries per (pixel, unit)
-constexpr int TB_OFFTAB = TC_TW * TB_NE * 2;       // 2688 B: uint16 offsets [px_t][hrl*21 + j]
-constexpr int TB_THREADS = 448;                    // warp 0 TMA, 1 MMA, 2-9 builders, 10-13 epilogue
+constexpr int TB_THREADS = 704;                    // warp 0 TMA, 1 MMA, 2-17 builders, 18-21 epilogue
 __host__ __device__ constexpr int tb_smem_bytes(int bst) {
-    return TB_SMEM_A + bst * 2 * TC_BBLK + TB_OFFTAB + TB_NBAR * 8 + 16 + 1024;
+    return TB_SMEM_A + bst * 2 * TC_BBLK + TB_NBAR * 8 + 16 + 1024;
+}
+
+// One builder thread's 36 columns (halo row HRL of the unit) of its tile pixel's A row, hi and lo,
+// as 18 packed 32-bit stores each.  K-major SW32 layout: element k of row r lives at
+// (k >> 4) * 4096 + r * 32 + ((((k >> 3) & 1) ^ ((r >> 2) & 1)) << 4) + (k & 7) * 2; bc0 / bc1 are the
+// row pointers pre-offset for logical 16-byte half 0 / 1, so every store has an immediate offset.
+template <int HRL>
+__device__ __forceinline__ void tb_store_row(unsigned char *h0, unsigned char *h1, unsigned char *l0,
+                                             unsigned char *l1, const float (&v)[TC_HW]) {
+#pragma unroll
+    for (int i = 0; i < TC_HW / 2; ++i) {
+        const int k = HRL * TC_HW + 2 * i;                        // even
+        const int off = (k >> 4) * 4096 + (k & 7) * 2;
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[2 * i] - __low2float(hi), v[2 * i + 1] - __high2float(hi));
+        if ((k >> 3) & 1) {
+            *reinterpret_cast<__nv_bfloat162 *>(h1 + off) = hi;
+            *reinterpret_cast<__nv_bfloat162 *>(l1 + off) = lo;
+        } else {
+            *reinterpret_cast<__nv_bfloat162 *>(h0 + off) = hi;
+            *reinterpret_cast<__nv_bfloat162 *>(l0 + off) = lo;
+        }
+    }
 }
 
 template <int WHICH>
@@ -304,8 +326,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sA = smem;                          // [stage][hl][9 k-steps][2 chunks][16 groups][8 x 16 B]
     unsigned char *sB = smem + TB_SMEM_A;              // [stage][hl][144 rows x 128 B] (SW128)
-    unsigned short *offtab = reinterpret_cast<unsigned short *>(sB + TB_NBST * 2 * TC_BBLK);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TB_NBST * 2 * TC_BBLK + TB_OFFTAB);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TB_NBST * 2 * TC_BBLK);
     uint64_t *a_full = bars, *a_empty = a_full + TB_NAST;
     uint64_t *b_full = a_empty + TB_NAST, *b_empty = b_full + TB_MAXBST;
     uint64_t *acc_full = b_empty + TB_MAXBST, *acc_empty = acc_full + TB_NACC;
@@ -319,17 +340,10 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
 
     if (tid == 0) {
         prefetch_tensormap(&moh); prefetch_tensormap(&mol);
-        for (int i = 0; i < TB_NAST; ++i) { mbar_init(&a_full[i], 256); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < TB_NAST; ++i) { mbar_init(&a_full[i], 512); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < TB_MAXBST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < TB_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_barrier_init();
-    }
-    // byte offset (without the row term and the swizzle bit) of band entry e = hrl*21 + j of a thread
-    // whose tile column is px: k = hrl*36 + px + j -> (k >> 4) * 4096 + ((k >> 3) & 1) * 16 + (k & 7) * 2
-    for (int i = tid; i < TC_TW * TB_NE; i += TB_THREADS) {
-        const int px = i / TB_NE, e = i % TB_NE;
-        const int k = (e / TC_DS) * TC_HW + px + (e % TC_DS);
-        offtab[i] = (unsigned short)((k >> 4) * 4096 + ((k >> 3) & 1) * 16 + (k & 7) * 2);
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tcgen05_fence_before();
@@ -398,82 +412,64 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                 umma_commit(&acc_full[ab]);
             }
         }
-    } else if (warp < 10) {
+    } else if (warp < 18) {
         // ===================== builders: banded gradOutput matrix A (hi / lo) =====================
-        const int tb = tid - 64;                   // 0..255
-        const int p = tb & 127, half = tb >> 7;    // tile pixel, which two halo rows of each unit
+        const int tb = tid - 64;                   // 0..511
+        const int p = tb & 127, hrl = tb >> 7;     // tile pixel; halo row of the unit (warp-uniform)
         const int py_t = p >> 4, px_t = p & 15;
-        const uint32_t row_off = p * 32;           // SW32 K-major: 32-byte rows, chunk ^= (row >> 2) & 1
         const uint32_t swz16 = ((p >> 2) & 1) << 4;
-        const uint32_t *mytab = reinterpret_cast<const uint32_t *>(offtab + px_t * TB_NE + half * 2 * TC_DS);
+        const int iplane = (int)plane;             // all tensors < 2^31 elements (checked by the C ABI)
         uint32_t ucount = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const TcTile T = tc_decode(t, nxt, nyt);
             const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
             const bool pix_ok = (yc < Hc) && (xc < Wc);
-            const float *gn = gout + (long)T.n * (TC_DS * TC_DS) * plane;
+            const int nbase = T.n * (TC_DS * TC_DS);
             for (int u = 0; u < TC_NU; ++u, ++ucount) {
                 const int as = ucount % TB_NAST;
-                // (1) issue all 42 gradOutput loads of this thread before touching shared memory
-                float v[2][TC_DS];
+                // (1) this thread's 36 columns: column qx holds band entry j = qx - px_t (0..20), else 0.
+                //     All loads are issued before shared memory is touched.
+                const int tjp = u * TC_UR + hrl - py_t;           // tj + 10 of this (pixel row, halo row) pair
+                bool row_ok = (tjp >= 0) && (tjp < TC_DS);
+                int off0, step, xs0 = 0;
+                if (WHICH == 1) {
+                    row_ok = row_ok && pix_ok;                    // gO at the output pixel itself
+                    off0 = ((nbase + tjp * TC_DS) * H + (2 * yc + T.py)) * W + (2 * xc + T.px);
+                    step = iplane;                                // next ti -> next plane
+                } else {
+                    const int ycs = T.yc0 - TC_DR + u * TC_UR + hrl;       // source pixel row (class coords)
+                    row_ok = row_ok && (ycs >= 0) && (ycs < Hc);
+                    xs0 = T.xc0 - TC_DR + px_t;                            // source column for j = 0
+                    // plane (20 - tjp, 20 - j), pixel (ycs, xs0 + j): j -> j+1 moves -1 plane, +2 in x
+                    off0 = ((nbase + (TC_DS - 1 - tjp) * TC_DS + (TC_DS - 1)) * H + (2 * ycs + T.py)) * W +
+                           (2 * xs0 + T.px);
+                    step = 2 - iplane;
+                }
+                if (!row_ok) off0 = 0;
+                float v[TC_HW];
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int hrl = half * 2 + hh;
-                    const int tjp = u * TC_UR + hrl - py_t;       // tj + 10 of this (pixel row, halo row) pair
-                    bool row_ok = (tjp >= 0) && (tjp < TC_DS);
-                    const float *src;
-                    long step;
-                    int xs0 = 0;
-                    if (WHICH == 1) {
-                        row_ok = row_ok && pix_ok;                // gO at the output pixel itself
-                        src = gn + (long)(tjp * TC_DS) * plane + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
-                        step = plane;                             // next ti -> next plane
-                    } else {
-                        const int ycs = T.yc0 - TC_DR + u * TC_UR + hrl;   // source pixel row (class coords)
-                        row_ok = row_ok && (ycs >= 0) && (ycs < Hc);
-                        xs0 = T.xc0 - TC_DR + px_t;                        // source column for j = 0
-                        // plane (20 - tjp, 20 - j), pixel (ycs, xs0 + j): j -> j+1 moves -1 plane, +2 in x
-                        src = gn + (long)((TC_DS - 1 - tjp) * TC_DS + (TC_DS - 1)) * plane +
-                              (long)(2 * ycs + T.py) * W + (2 * xs0 + T.px);
-                        step = 2 - plane;
-                    }
-#pragma unroll
-                    for (int j = 0; j < TC_DS; ++j) {
-                        const bool ok = row_ok && (WHICH == 1 || (xs0 + j >= 0 && xs0 + j < Wc));
-                        v[hh][j] = ok ? __ldg(src + j * step) : 0.f;
-                    }
+                for (int qx = 0; qx < TC_HW; ++qx) {
+                    const int j = qx - px_t;
+                    const bool ok = row_ok && ((unsigned)j < (unsigned)TC_DS) &&
+                                    (WHICH == 1 || ((unsigned)(xs0 + j) < (unsigned)Wc));
+                    v[qx] = ok ? __ldg(gout + (off0 + j * step)) : 0.f;
                 }
                 mbar_wait(&a_empty[as], ((ucount / TB_NAST) & 1) ^ 1);
-                // (2) zero this thread's half of the row: 16-byte chunks [9*half, 9*half + 9) of 18
-                unsigned char *ah = sA + as * TB_ASTG + row_off, *al = ah + TB_AHL;
-#pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    const int ch = half * 9 + i;                  // chunk: k-step ch >> 1, 16-byte half ch & 1
-                    const uint32_t zo = (ch >> 1) * 4096 + (((ch & 1) << 4) ^ swz16);   // physical half = logical ^ swizzle
-                    *reinterpret_cast<uint4 *>(ah + zo) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4 *>(al + zo) = make_uint4(0, 0, 0, 0);
-                }
-                // (3) scatter the band entries (offsets from the precomputed table)
-#pragma unroll
-                for (int e2 = 0; e2 < TC_DS; ++e2) {              // 21 pairs = 42 entries
-                    const uint32_t two = mytab[e2];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int e = 2 * e2 + q;                 // hh = e / 21, j = e % 21
-                        const float x = v[e / TC_DS][e % TC_DS];
-                        const __nv_bfloat16 h = __float2bfloat16_rn(x);
-                        const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-                        const uint32_t off = ((two >> (16 * q)) & 0xFFFFu) ^ swz16;
-                        *reinterpret_cast<unsigned short *>(ah + off) = __bfloat16_as_ushort(h);
-                        *reinterpret_cast<unsigned short *>(al + off) = __bfloat16_as_ushort(l);
-                    }
+                // (2) 36 packed stores (hi) + 36 (lo), immediate offsets
+                unsigned char *ah = sA + as * TB_ASTG + p * 32, *al = ah + TB_AHL;
+                unsigned char *h0 = ah + swz16, *h1 = ah + (16 - swz16), *l0 = al + swz16, *l1 = al + (16 - swz16);
+                switch (hrl) {
+                    case 0: tb_store_row<0>(h0, h1, l0, l1, v); break;
+                    case 1: tb_store_row<1>(h0, h1, l0, l1, v); break;
+                    case 2: tb_store_row<2>(h0, h1, l0, l1, v); break;
+                    default: tb_store_row<3>(h0, h1, l0, l1, v); break;
                 }
                 fence_proxy_async();          // generic-proxy writes -> visible to the tensor core
                 mbar_arrive(&a_full[as]);
             }
         }
     } else {
-        // ===================== epilogue (warps 10..13) =====================
+        // ===================== epilogue (warps 18..21) =====================
         const int quad = warp & 3;
         const int p = quad * 32 + lane;
         const int py_t = p >> 4, px_t = p & 15;
