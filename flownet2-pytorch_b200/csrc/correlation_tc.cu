@@ -278,10 +278,12 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 //   B = the other input's halo chunk from the prepass copy ([pixel][channel] bf16 = MN-major operand),
 //       one 64-channel block per TMA stage;
 //   3 MMAs (hi*hi, hi*lo, lo*hi) per k-step, N = 64 per instruction.
-// Roles (704 threads): warp 0 TMA, warp 1 MMA, warps 2-17 builders (FOUR threads per tile pixel, one
-// halo row each -- a single warp per scheduler ran its ~2000 dependent instructions per unit at IPC
-// ~0.2 and made the builder, not the tensor pipe, the bottleneck; each thread now writes its full
-// 36-column segment (zeros outside the band) with 36 packed immediate-offset stores), warps 18-21 epilogue.
+// Roles (704 threads): warp 0 TMA, warp 1 MMA, warps 2-17 builders, warps 18-21 epilogue.
+// Builders: FOUR threads per tile pixel = (halo-row pair) x (displacement half); a single warp per
+// scheduler ran ~2000 dependent instructions per unit at IPC ~0.2 and made the builder -- not the
+// tensor pipe -- the bottleneck.  Loads stay coalesced (lanes = pixels, one displacement plane per
+// instruction); the band positions a pixel row writes are the same for every unit, so the zero
+// columns of A are written ONCE at kernel start and the scatter offsets live in registers.
 // ------------------------------------------------------------------------------------------------
 constexpr int TB_KS = TC_N / 16;                   // 9 k-steps per unit
 constexpr int TB_AHL = TB_KS * 4096;               // 36864 B: one of {hi, lo} of a unit's A
@@ -294,28 +296,6 @@ __host__ __device__ constexpr int tb_smem_bytes(int bst) {
     return TB_SMEM_A + bst * 2 * TC_BBLK + TB_NBAR * 8 + 16 + 1024;
 }
 
-// One builder thread's 36 columns (halo row HRL of the unit) of its tile pixel's A row, hi and lo,
-// as 18 packed 32-bit stores each.  K-major SW32 layout: element k of row r lives at
-// (k >> 4) * 4096 + r * 32 + ((((k >> 3) & 1) ^ ((r >> 2) & 1)) << 4) + (k & 7) * 2; bc0 / bc1 are the
-// row pointers pre-offset for logical 16-byte half 0 / 1, so every store has an immediate offset.
-template <int HRL>
-__device__ __forceinline__ void tb_store_row(unsigned char *h0, unsigned char *h1, unsigned char *l0,
-                                             unsigned char *l1, const float (&v)[TC_HW]) {
-#pragma unroll
-    for (int i = 0; i < TC_HW / 2; ++i) {
-        const int k = HRL * TC_HW + 2 * i;                        // even
-        const int off = (k >> 4) * 4096 + (k & 7) * 2;
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[2 * i] - __low2float(hi), v[2 * i + 1] - __high2float(hi));
-        if ((k >> 3) & 1) {
-            *reinterpret_cast<__nv_bfloat162 *>(h1 + off) = hi;
-            *reinterpret_cast<__nv_bfloat162 *>(l1 + off) = lo;
-        } else {
-            *reinterpret_cast<__nv_bfloat162 *>(h0 + off) = hi;
-            *reinterpret_cast<__nv_bfloat162 *>(l0 + off) = lo;
-        }
-    }
-}
 
 template <int WHICH>
 __global__ void __launch_bounds__(TB_THREADS, 1)
@@ -345,6 +325,9 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
         for (int i = 0; i < TB_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_barrier_init();
     }
+    // columns of A outside a pixel row's band are zero for every unit: written once, here
+    for (int i = tid; i < TB_SMEM_A / 16; i += TB_THREADS) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
@@ -415,10 +398,25 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
     } else if (warp < 18) {
         // ===================== builders: banded gradOutput matrix A (hi / lo) =====================
         const int tb = tid - 64;                   // 0..511
-        const int p = tb & 127, hrl = tb >> 7;     // tile pixel; halo row of the unit (warp-uniform)
+        const int p = tb & 127, sub = tb >> 7;     // tile pixel; sub-task (warp-uniform)
+        const int hp = sub >> 1, jh = sub & 1;     // halo rows {2hp, 2hp+1}; displacements [11*jh, 11*jh + nj)
+        const int j0 = jh * 11, nj = jh ? 10 : 11;
         const int py_t = p >> 4, px_t = p & 15;
-        const uint32_t swz16 = ((p >> 2) & 1) << 4;
+        const uint32_t swz = (p >> 2) & 1;
         const int iplane = (int)plane;             // all tensors < 2^31 elements (checked by the C ABI)
+        // scatter offsets (unit-invariant): entry (hh, jj) -> k = (2hp+hh)*36 + px_t + j0 + jj
+        uint32_t offs[11];
+#pragma unroll
+        for (int jj = 0; jj < 11; ++jj) {
+            uint32_t two = 0;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t k = (2 * hp + hh) * TC_HW + px_t + j0 + jj;
+                const uint32_t off = (k >> 4) * 4096 + p * 32 + ((((k >> 3) & 1) ^ swz) << 4) + (k & 7) * 2;
+                two |= off << (16 * hh);
+            }
+            offs[jj] = two;
+        }
         uint32_t ucount = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const TcTile T = tc_decode(t, nxt, nyt);
@@ -427,42 +425,48 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
             const int nbase = T.n * (TC_DS * TC_DS);
             for (int u = 0; u < TC_NU; ++u, ++ucount) {
                 const int as = ucount % TB_NAST;
-                // (1) this thread's 36 columns: column qx holds band entry j = qx - px_t (0..20), else 0.
-                //     All loads are issued before shared memory is touched.
-                const int tjp = u * TC_UR + hrl - py_t;           // tj + 10 of this (pixel row, halo row) pair
-                bool row_ok = (tjp >= 0) && (tjp < TC_DS);
-                int off0, step, xs0 = 0;
-                if (WHICH == 1) {
-                    row_ok = row_ok && pix_ok;                    // gO at the output pixel itself
-                    off0 = ((nbase + tjp * TC_DS) * H + (2 * yc + T.py)) * W + (2 * xc + T.px);
-                    step = iplane;                                // next ti -> next plane
-                } else {
-                    const int ycs = T.yc0 - TC_DR + u * TC_UR + hrl;       // source pixel row (class coords)
-                    row_ok = row_ok && (ycs >= 0) && (ycs < Hc);
-                    xs0 = T.xc0 - TC_DR + px_t;                            // source column for j = 0
-                    // plane (20 - tjp, 20 - j), pixel (ycs, xs0 + j): j -> j+1 moves -1 plane, +2 in x
-                    off0 = ((nbase + (TC_DS - 1 - tjp) * TC_DS + (TC_DS - 1)) * H + (2 * ycs + T.py)) * W +
-                           (2 * xs0 + T.px);
-                    step = 2 - iplane;
-                }
-                if (!row_ok) off0 = 0;
-                float v[TC_HW];
+                float v[2][11];
 #pragma unroll
-                for (int qx = 0; qx < TC_HW; ++qx) {
-                    const int j = qx - px_t;
-                    const bool ok = row_ok && ((unsigned)j < (unsigned)TC_DS) &&
-                                    (WHICH == 1 || ((unsigned)(xs0 + j) < (unsigned)Wc));
-                    v[qx] = ok ? __ldg(gout + (off0 + j * step)) : 0.f;
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int hrl = 2 * hp + hh;
+                    const int tjp = u * TC_UR + hrl - py_t;       // tj + 10 of this (pixel row, halo row) pair
+                    bool row_ok = (tjp >= 0) && (tjp < TC_DS);
+                    int off0, step, xs0 = 0;
+                    if (WHICH == 1) {
+                        row_ok = row_ok && pix_ok;                // gO at the output pixel itself
+                        off0 = ((nbase + tjp * TC_DS + j0) * H + (2 * yc + T.py)) * W + (2 * xc + T.px);
+                        step = iplane;                            // next ti -> next plane
+                    } else {
+                        const int ycs = T.yc0 - TC_DR + u * TC_UR + hrl;   // source pixel row (class coords)
+                        row_ok = row_ok && (ycs >= 0) && (ycs < Hc);
+                        xs0 = T.xc0 - TC_DR + px_t + j0;                   // source column for jj = 0
+                        // plane (20 - tjp, 20 - j), pixel (ycs, xs0 + jj): j -> j+1 moves -1 plane, +2 in x
+                        off0 = ((nbase + (TC_DS - 1 - tjp) * TC_DS + (TC_DS - 1 - j0)) * H + (2 * ycs + T.py)) * W +
+                               (2 * xs0 + T.px);
+                        step = 2 - iplane;
+                    }
+                    if (!row_ok) off0 = 0;
+#pragma unroll
+                    for (int jj = 0; jj < 11; ++jj) {
+                        const bool ok = row_ok && (jj < nj) && (WHICH == 1 || ((unsigned)(xs0 + jj) < (unsigned)Wc));
+                        v[hh][jj] = ok ? __ldg(gout + (off0 + jj * step)) : 0.f;
+                    }
                 }
                 mbar_wait(&a_empty[as], ((ucount / TB_NAST) & 1) ^ 1);
-                // (2) 36 packed stores (hi) + 36 (lo), immediate offsets
-                unsigned char *ah = sA + as * TB_ASTG + p * 32, *al = ah + TB_AHL;
-                unsigned char *h0 = ah + swz16, *h1 = ah + (16 - swz16), *l0 = al + swz16, *l1 = al + (16 - swz16);
-                switch (hrl) {
-                    case 0: tb_store_row<0>(h0, h1, l0, l1, v); break;
-                    case 1: tb_store_row<1>(h0, h1, l0, l1, v); break;
-                    case 2: tb_store_row<2>(h0, h1, l0, l1, v); break;
-                    default: tb_store_row<3>(h0, h1, l0, l1, v); break;
+                unsigned char *ah = sA + as * TB_ASTG, *al = ah + TB_AHL;
+#pragma unroll
+                for (int jj = 0; jj < 11; ++jj) {
+                    if (jj < nj) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const float x = v[hh][jj];
+                            const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                            const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+                            const uint32_t off = (offs[jj] >> (16 * hh)) & 0xFFFFu;
+                            *reinterpret_cast<unsigned short *>(ah + off) = __bfloat16_as_ushort(h);
+                            *reinterpret_cast<unsigned short *>(al + off) = __bfloat16_as_ushort(l);
+                        }
+                    }
                 }
                 fence_proxy_async();          // generic-proxy writes -> visible to the tensor core
                 mbar_arrive(&a_full[as]);
