@@ -1,0 +1,18 @@
+#!/bin/bash
+# full validation + numbers for profiles/: tests, smoke, bench (both arms), op comparison, ncu launch list + full capture
+TAG=${1:-r1g}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1; nproc >> gpurun_out/${TAG}_gpu.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log
+timeout 200 python __graft_entry__.py --smoke 2>&1 | tail -1
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_ours.json 2> gpurun_out/${TAG}_bench_ours.err; echo "bench rc=$?"
+python - <<PY
+import json
+d=json.load(open("gpurun_out/${TAG}_bench_ours.json"))
+print({k:d[k] for k in ("value","ms_per_step","kernels","roofline","e2e","gpu_launches","clocks")})
+print(d.get("flownet2")); print(d.get("ops"))
+PY
+timeout 600 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; echo "benchref rc=$?"
+timeout 600 python tools/compare_ref.py --quick > gpurun_out/${TAG}_compare.json 2> gpurun_out/${TAG}_compare.err; echo "compare rc=$?"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-extras > gpurun_out/${TAG}_bench_under_ncu.log 2>&1; echo "ncu-list rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"corr_|resample2d_|channelnorm_" -c 12 -o gpurun_out/${TAG}_prof python tools/prof_ops.py all 1 > gpurun_out/${TAG}_prof.log 2>&1; echo "ncu-full rc=$?"
