@@ -277,8 +277,7 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 //       no-swizzle layout made the 2-byte band scatter 4-way bank conflicted: 70 % of wavefronts);
 //   B = the other input's halo chunk from the prepass copy ([pixel][channel] bf16 = MN-major operand),
 //       one 64-channel block per TMA stage;
-//   3 MMAs (hi*hi, hi*lo, lo*hi) per k-step, N = C (<= 256) per instruction: the unit's 144 K indices are
-//   staged in 3 groups of 48 (12 halo columns x 4 rows), each stage holding all C/64 channel blocks.
+//   3 MMAs (hi*hi, hi*lo, lo*hi) per k-step, N = 64 per instruction.
 // Roles (704 threads): warp 0 TMA, warp 1 MMA, warps 2-17 builders, warps 18-21 epilogue.
 // Builders: FOUR threads per tile pixel = (halo-row pair) x (displacement half); a single warp per
 // scheduler ran ~2000 dependent instructions per unit at IPC ~0.2 and made the builder -- not the
@@ -605,8 +604,8 @@ static int launch_bwd_tc(const __nv_bfloat16 *oh, const __nv_bfloat16 *ol, const
                          const CorrParams &p, cudaStream_t st) {
     CUtensorMap moh, mol;
     int rc;
-    if ((rc = make_class_map(&moh, oh, p, TB_GW, TC_UR))) return rc;     // one K group: 12 halo columns x 4 rows
-    if ((rc = make_class_map(&mol, ol, p, TB_GW, TC_UR))) return rc;
+    if ((rc = make_class_map(&moh, oh, p, TC_HW, TC_UR))) return rc;
+    if ((rc = make_class_map(&mol, ol, p, TC_HW, TC_UR))) return rc;
     const int Hc = p.H / 2, Wc = p.W / 2;
     const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
     const int ntiles = p.B * 4 * nxt * nyt;
