@@ -286,23 +286,16 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 // columns of A are written ONCE at kernel start and the scatter offsets live in registers.
 // ------------------------------------------------------------------------------------------------
 constexpr int TB_KS = TC_N / 16;                   // 9 k-steps per unit
-constexpr int TB_NG = 3;                           // K groups per unit: halo columns [12g, 12g+12) x 4 rows = 48
-constexpr int TB_GW = TC_HW / TB_NG;               // 12 halo columns per group
-constexpr int TB_GK = TC_UR * TB_GW;               // 48 K indices (3 k-steps) per group
 constexpr int TB_AHL = TB_KS * 4096;               // 36864 B: one of {hi, lo} of a unit's A
-constexpr int TB_SMEM_A = 2 * TB_AHL;              // 73728 B: ONE unit of A, handed over group by group
-constexpr int TB_BBLK = TB_GK * 128;               // 6144 B: one 64-channel block of a group's B rows
-constexpr int TB_MAXBST = 4, TB_NACC = 2;
-constexpr int TB_NBAR = 2 * TB_NG + 2 * TB_MAXBST + 2 * TB_NACC;
+constexpr int TB_ASTG = 2 * TB_AHL;                // 73728 B per A stage
+constexpr int TB_NAST = 2, TB_MAXBST = 4, TB_NACC = 2;
+constexpr int TB_SMEM_A = TB_NAST * TB_ASTG;       // 147456
+constexpr int TB_NBAR = 2 * TB_NAST + 2 * TB_MAXBST + 2 * TB_NACC;
 constexpr int TB_THREADS = 704;                    // warp 0 TMA, 1 MMA, 2-17 builders, 18-21 epilogue
-__host__ __device__ constexpr int tb_smem_bytes(int ncb, int bst) {
-    return TB_SMEM_A + bst * 2 * ncb * TB_BBLK + TB_NBAR * 8 + 16 + 1024;
+__host__ __device__ constexpr int tb_smem_bytes(int bst) {
+    return TB_SMEM_A + bst * 2 * TC_BBLK + TB_NBAR * 8 + 16 + 1024;
 }
-// K index of halo position (row hrl of the unit, column qx): grouped by column so that one TMA box
-// (64 channels x 12 columns x 4 rows) is one contiguous K range
-__host__ __device__ constexpr uint32_t tb_kindex(uint32_t hrl, uint32_t qx) {
-    return (qx / TB_GW) * TB_GK + hrl * TB_GW + (qx % TB_GW);
-}
+
 
 template <int WHICH>
 __global__ void __launch_bounds__(TB_THREADS, 1)
@@ -310,24 +303,24 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                    const float *__restrict__ gout, float *__restrict__ gin, int B, int C, int H, int W,
                    int ntiles, int TB_NBST, int hint) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sA = smem;                          // [stage][hl][9 k-steps][2 chunks][16 groups][8 x 16 B]
+    unsigned char *sB = smem + TB_SMEM_A;              // [stage][hl][144 rows x 128 B] (SW128)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TB_NBST * 2 * TC_BBLK);
+    uint64_t *a_full = bars, *a_empty = a_full + TB_NAST;
+    uint64_t *b_full = a_empty + TB_NAST, *b_empty = b_full + TB_MAXBST;
+    uint64_t *acc_full = b_empty + TB_MAXBST, *acc_empty = acc_full + TB_NACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + TB_NBAR);
+
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Hc = H >> 1, Wc = W >> 1;
     const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
     const int ncb = C / TC_KB;
     const long plane = (long)H * W;
-    const int bstage = 2 * ncb * TB_BBLK;              // bytes of one B stage: [hl][ncb][48 rows x 128 B]
-    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char *sA = smem;                          // [hl][9 k-step blocks][128 rows x 32 B] (SW32), 3 groups of 3 blocks
-    unsigned char *sB = smem + TB_SMEM_A;              // [stage][hl][ncb][48 rows x 128 B] (SW128, MN-major)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TB_NBST * bstage);
-    uint64_t *a_full = bars, *a_empty = a_full + TB_NG;
-    uint64_t *b_full = a_empty + TB_NG, *b_empty = b_full + TB_MAXBST;
-    uint64_t *acc_full = b_empty + TB_MAXBST, *acc_empty = acc_full + TB_NACC;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + TB_NBAR);
 
     if (tid == 0) {
         prefetch_tensormap(&moh); prefetch_tensormap(&mol);
-        for (int i = 0; i < TB_NG; ++i) { mbar_init(&a_full[i], 512); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < TB_NAST; ++i) { mbar_init(&a_full[i], 512); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < TB_MAXBST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < TB_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_barrier_init();
@@ -342,7 +335,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer: the other input's halo chunks, one K group per stage =====================
+        // ===================== TMA producer: the other input's halo chunks =====================
         if (lane == 0) {
             uint32_t bcount = 0;
             const uint64_t pol = l2_policy_evict_last();
@@ -354,52 +347,50 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                 const TcTile T = tc_decode(t, nxt, nyt);
                 const int img = T.n * 4 + T.py * 2 + T.px;
                 for (int u = 0; u < TC_NU; ++u)
-                    for (int g = 0; g < TB_NG; ++g, ++bcount) {
+                    for (int j = 0; j < ncb; ++j, ++bcount) {
                         const int s = bcount % TB_NBST;
                         mbar_wait(&b_empty[s], ((bcount / TB_NBST) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&b_full[s], (uint32_t)bstage);
-                        unsigned char *dst = sB + s * bstage;
-                        for (int j = 0; j < ncb; ++j) {
-                            load(dst + j * TB_BBLK, &moh, &b_full[s], j * TC_KB, T.xc0 - TC_DR + g * TB_GW,
-                                 T.yc0 - TC_DR + u * TC_UR, img);
-                            load(dst + (ncb + j) * TB_BBLK, &mol, &b_full[s], j * TC_KB, T.xc0 - TC_DR + g * TB_GW,
-                                 T.yc0 - TC_DR + u * TC_UR, img);
-                        }
+                        mbar_arrive_expect_tx(&b_full[s], 2 * TC_BBLK);
+                        load(sB + (s * 2 + 0) * TC_BBLK, &moh, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
+                                    T.yc0 - TC_DR + u * TC_UR, img);
+                        load(sB + (s * 2 + 1) * TC_BBLK, &mol, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
+                                    T.yc0 - TC_DR + u * TC_UR, img);
                     }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer: N = C columns per instruction =====================
+        // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_f32(128, C, 1);   // B MN-major
+            const uint32_t idesc = umma_idesc_bf16_f32(128, TC_KB, 1);   // N = 64, B MN-major
             uint32_t bcount = 0, ucount = 0, tcount = 0;
-            const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + TB_AHL;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
                 const int ab = tcount % TB_NACC;
                 mbar_wait(&acc_empty[ab], ((tcount / TB_NACC) & 1) ^ 1);
                 tcgen05_fence_after();
-                const uint32_t d = tmem_base + ab * 256;
                 for (int u = 0; u < TC_NU; ++u, ++ucount) {
-                    for (int g = 0; g < TB_NG; ++g, ++bcount) {
+                    const int as = ucount % TB_NAST;
+                    mbar_wait(&a_full[as], (ucount / TB_NAST) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t a_hi = smem_u32(sA + as * TB_ASTG), a_lo = a_hi + TB_AHL;
+                    for (int j = 0; j < ncb; ++j, ++bcount) {
                         const int s = bcount % TB_NBST;
-                        mbar_wait(&a_full[g], ucount & 1);
                         mbar_wait(&b_full[s], (bcount / TB_NBST) & 1);
                         tcgen05_fence_after();
-                        const uint32_t bbase = smem_u32(sB + s * bstage);
-                        const uint64_t bh = umma_desc_mn_sw128(bbase, TB_BBLK);
-                        const uint64_t bl = umma_desc_mn_sw128(bbase + ncb * TB_BBLK, TB_BBLK);
+                        const uint64_t bh = umma_desc_mn_sw128(smem_u32(sB + (s * 2 + 0) * TC_BBLK), TC_BBLK);
+                        const uint64_t bl = umma_desc_mn_sw128(smem_u32(sB + (s * 2 + 1) * TC_BBLK), TC_BBLK);
+                        const uint32_t d = tmem_base + ab * 256 + j * TC_KB;
 #pragma unroll
-                        for (int ks = 0; ks < TB_GK / 16; ++ks) {
-                            const uint64_t ah = umma_desc_k_sw32(a_hi + (g * 3 + ks) * 4096);
-                            const uint64_t al = umma_desc_k_sw32(a_lo + (g * 3 + ks) * 4096);
+                        for (int ks = 0; ks < TB_KS; ++ks) {
+                            const uint64_t ah = umma_desc_k_sw32(a_hi + ks * 4096);
+                            const uint64_t al = umma_desc_k_sw32(a_lo + ks * 4096);
                             const uint64_t kadv = (uint64_t)((ks * 16 * 128) >> 4);
-                            umma_bf16_ss(d, ah, bh + kadv, idesc, (u | g | ks) != 0);
+                            umma_bf16_ss(d, ah, bh + kadv, idesc, (u | ks) != 0);
                             umma_bf16_ss(d, ah, bl + kadv, idesc, 1);
                             umma_bf16_ss(d, al, bh + kadv, idesc, 1);
                         }
                         umma_commit(&b_empty[s]);
-                        umma_commit(&a_empty[g]);
                     }
+                    umma_commit(&a_empty[as]);
                 }
                 umma_commit(&acc_full[ab]);
             }
@@ -413,20 +404,18 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
         const int py_t = p >> 4, px_t = p & 15;
         const uint32_t swz = (p >> 2) & 1;
         const int iplane = (int)plane;             // all tensors < 2^31 elements (checked by the C ABI)
-        // scatter offsets (unit-invariant): entry (hh, jj) sits at halo (row 2hp+hh, column px_t + j0 + jj)
-        uint32_t offs[11], grp = 0;                // grp: 2 bits per jj = K group of that column
+        // scatter offsets (unit-invariant): entry (hh, jj) -> k = (2hp+hh)*36 + px_t + j0 + jj
+        uint32_t offs[11];
 #pragma unroll
         for (int jj = 0; jj < 11; ++jj) {
             uint32_t two = 0;
-            const uint32_t qx = px_t + j0 + jj;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                const uint32_t k = tb_kindex(2 * hp + hh, qx);
+                const uint32_t k = (2 * hp + hh) * TC_HW + px_t + j0 + jj;
                 const uint32_t off = (k >> 4) * 4096 + p * 32 + ((((k >> 3) & 1) ^ swz) << 4) + (k & 7) * 2;
                 two |= off << (16 * hh);
             }
             offs[jj] = two;
-            grp |= (qx / TB_GW) << (2 * jj);
         }
         uint32_t ucount = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -435,6 +424,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
             const bool pix_ok = (yc < Hc) && (xc < Wc);
             const int nbase = T.n * (TC_DS * TC_DS);
             for (int u = 0; u < TC_NU; ++u, ++ucount) {
+                const int as = ucount % TB_NAST;
                 float v[2][11];
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -462,27 +452,24 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                         v[hh][jj] = ok ? __ldg(gout + (off0 + jj * step)) : 0.f;
                     }
                 }
-                unsigned char *ah = sA, *al = sA + TB_AHL;
-#pragma unroll 1
-                for (int g = 0; g < TB_NG; ++g) {
-                    mbar_wait(&a_empty[g], (ucount & 1) ^ 1);     // the MMAs of the previous unit's group g are done
+                mbar_wait(&a_empty[as], ((ucount / TB_NAST) & 1) ^ 1);
+                unsigned char *ah = sA + as * TB_ASTG, *al = ah + TB_AHL;
 #pragma unroll
-                    for (int jj = 0; jj < 11; ++jj) {
-                        if (jj < nj && ((grp >> (2 * jj)) & 3u) == (uint32_t)g) {
+                for (int jj = 0; jj < 11; ++jj) {
+                    if (jj < nj) {
 #pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {
-                                const float x = v[hh][jj];
-                                const __nv_bfloat16 h = __float2bfloat16_rn(x);
-                                const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-                                const uint32_t off = (offs[jj] >> (16 * hh)) & 0xFFFFu;
-                                *reinterpret_cast<unsigned short *>(ah + off) = __bfloat16_as_ushort(h);
-                                *reinterpret_cast<unsigned short *>(al + off) = __bfloat16_as_ushort(l);
-                            }
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const float x = v[hh][jj];
+                            const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                            const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+                            const uint32_t off = (offs[jj] >> (16 * hh)) & 0xFFFFu;
+                            *reinterpret_cast<unsigned short *>(ah + off) = __bfloat16_as_ushort(h);
+                            *reinterpret_cast<unsigned short *>(al + off) = __bfloat16_as_ushort(l);
                         }
                     }
-                    fence_proxy_async();      // generic-proxy writes -> visible to the tensor core
-                    mbar_arrive(&a_full[g]);
                 }
+                fence_proxy_async();          // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(&a_full[as]);
             }
         }
     } else {
@@ -613,12 +600,11 @@ static int launch_bwd_tc(const __nv_bfloat16 *oh, const __nv_bfloat16 *ol, const
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     auto kern = corr_bwd_tc_kernel<WHICH>;
-    const int ncb = p.C / TC_KB;
     int bst = 2;
-    while (bst < TB_MAXBST && tb_smem_bytes(ncb, bst + 1) <= TC_SMEM_MAX) ++bst;
+    while (bst < TB_MAXBST && tb_smem_bytes(bst + 1) <= TC_SMEM_MAX) ++bst;
     bst = tc_env_int("FN2B200_TC_BST", bst, 2, bst);
     const int hint = tc_env_int("FN2B200_TC_HINT", 1, 0, 1);
-    const int smem = tb_smem_bytes(ncb, bst);
+    const int smem = tb_smem_bytes(bst);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "correlation_backward(tc): smem attribute (%s)", cudaGetErrorString(e));
     const int grid = ntiles < sms ? ntiles : sms;
