@@ -417,52 +417,40 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
             }
             offs[jj] = two;
         }
-        // gather(): the 22 gradOutput values of unit (TT, uu) for this thread -> dst (all loads in flight)
-        auto gather = [&](const TcTile &TT, int uu, float (&dst)[2][11]) {
-            const int yc = TT.yc0 + py_t, xc = TT.xc0 + px_t;
-            const bool pix_ok = (yc < Hc) && (xc < Wc);
-            const int nbase = TT.n * (TC_DS * TC_DS);
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int hrl = 2 * hp + hh;
-                const int tjp = uu * TC_UR + hrl - py_t;          // tj + 10 of this (pixel row, halo row) pair
-                bool row_ok = (tjp >= 0) && (tjp < TC_DS);
-                int off0, step, xs0 = 0;
-                if (WHICH == 1) {
-                    row_ok = row_ok && pix_ok;                    // gO at the output pixel itself
-                    off0 = ((nbase + tjp * TC_DS + j0) * H + (2 * yc + TT.py)) * W + (2 * xc + TT.px);
-                    step = iplane;                                // next ti -> next plane
-                } else {
-                    const int ycs = TT.yc0 - TC_DR + uu * TC_UR + hrl;     // source pixel row (class coords)
-                    row_ok = row_ok && (ycs >= 0) && (ycs < Hc);
-                    xs0 = TT.xc0 - TC_DR + px_t + j0;                      // source column for jj = 0
-                    // plane (20 - tjp, 20 - j), pixel (ycs, xs0 + jj): j -> j+1 moves -1 plane, +2 in x
-                    off0 = ((nbase + (TC_DS - 1 - tjp) * TC_DS + (TC_DS - 1 - j0)) * H + (2 * ycs + TT.py)) * W +
-                           (2 * xs0 + TT.px);
-                    step = 2 - iplane;
-                }
-                if (!row_ok) off0 = 0;
-#pragma unroll
-                for (int jj = 0; jj < 11; ++jj) {
-                    const bool ok = row_ok && (jj < nj) && (WHICH == 1 || ((unsigned)(xs0 + jj) < (unsigned)Wc));
-                    dst[hh][jj] = ok ? __ldg(gout + (off0 + jj * step)) : 0.f;
-                }
-            }
-        };
-        // Software pipeline: the loads of unit n+1 are issued BEFORE unit n is scattered, so the DRAM
-        // round trip of gradOutput (streamed once per launch) overlaps the scatter and the barrier wait
-        // instead of being paid by all 16 builder warps at the same time.
         uint32_t ucount = 0;
-        float v[2][11], vn[2][11];
-        if ((int)blockIdx.x < ntiles) gather(tc_decode(blockIdx.x, nxt, nyt), 0, v);
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const TcTile T = tc_decode(t, nxt, nyt);
+            const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
+            const bool pix_ok = (yc < Hc) && (xc < Wc);
+            const int nbase = T.n * (TC_DS * TC_DS);
             for (int u = 0; u < TC_NU; ++u, ++ucount) {
                 const int as = ucount % TB_NAST;
-                if (u + 1 < TC_NU) {
-                    gather(T, u + 1, vn);
-                } else if (t + (int)gridDim.x < ntiles) {
-                    gather(tc_decode(t + gridDim.x, nxt, nyt), 0, vn);
+                float v[2][11];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int hrl = 2 * hp + hh;
+                    const int tjp = u * TC_UR + hrl - py_t;       // tj + 10 of this (pixel row, halo row) pair
+                    bool row_ok = (tjp >= 0) && (tjp < TC_DS);
+                    int off0, step, xs0 = 0;
+                    if (WHICH == 1) {
+                        row_ok = row_ok && pix_ok;                // gO at the output pixel itself
+                        off0 = ((nbase + tjp * TC_DS + j0) * H + (2 * yc + T.py)) * W + (2 * xc + T.px);
+                        step = iplane;                            // next ti -> next plane
+                    } else {
+                        const int ycs = T.yc0 - TC_DR + u * TC_UR + hrl;   // source pixel row (class coords)
+                        row_ok = row_ok && (ycs >= 0) && (ycs < Hc);
+                        xs0 = T.xc0 - TC_DR + px_t + j0;                   // source column for jj = 0
+                        // plane (20 - tjp, 20 - j), pixel (ycs, xs0 + jj): j -> j+1 moves -1 plane, +2 in x
+                        off0 = ((nbase + (TC_DS - 1 - tjp) * TC_DS + (TC_DS - 1 - j0)) * H + (2 * ycs + T.py)) * W +
+                               (2 * xs0 + T.px);
+                        step = 2 - iplane;
+                    }
+                    if (!row_ok) off0 = 0;
+#pragma unroll
+                    for (int jj = 0; jj < 11; ++jj) {
+                        const bool ok = row_ok && (jj < nj) && (WHICH == 1 || ((unsigned)(xs0 + jj) < (unsigned)Wc));
+                        v[hh][jj] = ok ? __ldg(gout + (off0 + jj * step)) : 0.f;
+                    }
                 }
                 mbar_wait(&a_empty[as], ((ucount / TB_NAST) & 1) ^ 1);
                 unsigned char *ah = sA + as * TB_ASTG, *al = ah + TB_AHL;
@@ -482,10 +470,6 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                 }
                 fence_proxy_async();          // generic-proxy writes -> visible to the tensor core
                 mbar_arrive(&a_full[as]);
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-                    for (int jj = 0; jj < 11; ++jj) v[hh][jj] = vn[hh][jj];
             }
         }
     } else {
