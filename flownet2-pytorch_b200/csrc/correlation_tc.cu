@@ -301,7 +301,7 @@ template <int WHICH>
 __global__ void __launch_bounds__(TB_THREADS, 1)
 corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constant__ CUtensorMap mol,
                    const float *__restrict__ gout, float *__restrict__ gin, int B, int C, int H, int W,
-                   int ntiles, int TB_NBST, int hint) {
+                   int ntiles, int TB_NBST, int hint, long long *__restrict__ dbg) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sA = smem;                          // [stage][hl][9 k-steps][2 chunks][16 groups][8 x 16 B]
@@ -369,7 +369,10 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                 tcgen05_fence_after();
                 for (int u = 0; u < TC_NU; ++u, ++ucount) {
                     const int as = ucount % TB_NAST;
+                    const bool rec = dbg && blockIdx.x == 0 && ucount < 64;
+                    if (rec) dbg[ucount * 8 + 4] = clock64();
                     mbar_wait(&a_full[as], (ucount / TB_NAST) & 1);
+                    if (rec) dbg[ucount * 8 + 5] = clock64();
                     tcgen05_fence_after();
                     const uint32_t a_hi = smem_u32(sA + as * TB_ASTG), a_lo = a_hi + TB_AHL;
                     for (int j = 0; j < ncb; ++j, ++bcount) {
@@ -391,6 +394,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                         umma_commit(&b_empty[s]);
                     }
                     umma_commit(&a_empty[as]);
+                    if (rec) dbg[ucount * 8 + 6] = clock64();
                 }
                 umma_commit(&acc_full[ab]);
             }
@@ -452,7 +456,10 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                         v[hh][jj] = ok ? __ldg(gout + (off0 + jj * step)) : 0.f;
                     }
                 }
+                const bool rec = dbg && blockIdx.x == 0 && tb == 0 && ucount < 64;
+                if (rec) dbg[ucount * 8 + 0] = clock64();
                 mbar_wait(&a_empty[as], ((ucount / TB_NAST) & 1) ^ 1);
+                if (rec) dbg[ucount * 8 + 1] = clock64();
                 unsigned char *ah = sA + as * TB_ASTG, *al = ah + TB_AHL;
 #pragma unroll
                 for (int jj = 0; jj < 11; ++jj) {
@@ -469,7 +476,9 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                     }
                 }
                 fence_proxy_async();          // generic-proxy writes -> visible to the tensor core
+                if (rec) dbg[ucount * 8 + 2] = clock64();
                 mbar_arrive(&a_full[as]);
+                if (rec) dbg[ucount * 8 + 3] = clock64();
             }
         }
     } else {
@@ -608,7 +617,9 @@ static int launch_bwd_tc(const __nv_bfloat16 *oh, const __nv_bfloat16 *ol, const
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "correlation_backward(tc): smem attribute (%s)", cudaGetErrorString(e));
     const int grid = ntiles < sms ? ntiles : sms;
-    kern<<<grid, TB_THREADS, smem, st>>>(moh, mol, gout, gin, p.B, p.C, p.H, p.W, ntiles, bst, hint);
+    long long *dbg = nullptr;
+    if (const char *e = getenv("FN2B200_TC_DBG")) dbg = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
+    kern<<<grid, TB_THREADS, smem, st>>>(moh, mol, gout, gin, p.B, p.C, p.H, p.W, ntiles, bst, hint, dbg);
     count_launch();
     return check_launch("correlation_backward(tc)");
 }
