@@ -152,8 +152,8 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (converged warp, one elected lane issues) =====================
+        {
             uint32_t bcount = 0;
             int it = 0;
             const uint64_t pol = l2_policy_evict_last();
@@ -166,25 +166,31 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
                 const int img = T.n * 4 + T.py * 2 + T.px;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&a_empty[kb], (it & 1) ^ 1);
-                    mbar_arrive_expect_tx(&a_full[kb], 2 * TC_ABLK);
-                    load(sA + (0 * nkb + kb) * TC_ABLK, &m1h, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
-                    load(sA + (1 * nkb + kb) * TC_ABLK, &m1l, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(&a_full[kb], 2 * TC_ABLK);
+                        load(sA + (0 * nkb + kb) * TC_ABLK, &m1h, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
+                        load(sA + (1 * nkb + kb) * TC_ABLK, &m1l, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
+                    }
+                    __syncwarp();
                 }
                 for (int u = 0; u < TC_NU; ++u)
                     for (int kb = 0; kb < nkb; ++kb, ++bcount) {
                         const int s = bcount % TC_BST;
                         mbar_wait(&b_empty[s], ((bcount / TC_BST) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&b_full[s], 2 * TC_BBLK);
-                        load(sB + (s * 2 + 0) * TC_BBLK, &m2h, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
-                                    T.yc0 - TC_DR + u * TC_UR, img);
-                        load(sB + (s * 2 + 1) * TC_BBLK, &m2l, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
-                                    T.yc0 - TC_DR + u * TC_UR, img);
+                        if (elect_one_sync()) {
+                            mbar_arrive_expect_tx(&b_full[s], 2 * TC_BBLK);
+                            load(sB + (s * 2 + 0) * TC_BBLK, &m2h, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
+                                 T.yc0 - TC_DR + u * TC_UR, img);
+                            load(sB + (s * 2 + 1) * TC_BBLK, &m2l, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
+                                 T.yc0 - TC_DR + u * TC_UR, img);
+                        }
+                        __syncwarp();
                     }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+        {
             const uint32_t idesc = umma_idesc_bf16_f32(128, TC_N);
             uint32_t bcount = 0, acount = 0;
             int it = 0;
@@ -199,20 +205,23 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
                         const int s = bcount % TC_BST;
                         mbar_wait(&b_full[s], (bcount / TC_BST) & 1);
                         tcgen05_fence_after();
-                        const uint64_t ah = umma_desc_k_sw128(smem_u32(sA + (0 * nkb + kb) * TC_ABLK));
-                        const uint64_t al = umma_desc_k_sw128(smem_u32(sA + (1 * nkb + kb) * TC_ABLK));
-                        const uint64_t bh = umma_desc_k_sw128(smem_u32(sB + (s * 2 + 0) * TC_BBLK));
-                        const uint64_t bl = umma_desc_k_sw128(smem_u32(sB + (s * 2 + 1) * TC_BBLK));
+                        if (elect_one_sync()) {
+                            const uint64_t ah = umma_desc_k_sw128(smem_u32(sA + (0 * nkb + kb) * TC_ABLK));
+                            const uint64_t al = umma_desc_k_sw128(smem_u32(sA + (1 * nkb + kb) * TC_ABLK));
+                            const uint64_t bh = umma_desc_k_sw128(smem_u32(sB + (s * 2 + 0) * TC_BBLK));
+                            const uint64_t bl = umma_desc_k_sw128(smem_u32(sB + (s * 2 + 1) * TC_BBLK));
 #pragma unroll
-                        for (int ks = 0; ks < TC_KB / 16; ++ks) {
-                            umma_bf16_ss(d, ah + 2 * ks, bh + 2 * ks, idesc, (kb | ks) != 0);
-                            umma_bf16_ss(d, ah + 2 * ks, bl + 2 * ks, idesc, 1);
-                            umma_bf16_ss(d, al + 2 * ks, bh + 2 * ks, idesc, 1);
+                            for (int ks = 0; ks < TC_KB / 16; ++ks) {
+                                umma_bf16_ss(d, ah + 2 * ks, bh + 2 * ks, idesc, (kb | ks) != 0);
+                                umma_bf16_ss(d, ah + 2 * ks, bl + 2 * ks, idesc, 1);
+                                umma_bf16_ss(d, al + 2 * ks, bh + 2 * ks, idesc, 1);
+                            }
+                            umma_commit(&b_empty[s]);                    // stage may be refilled
+                            if (u == TC_NU - 1) umma_commit(&a_empty[kb]);  // A block free for the next tile
+                            if (kb == nkb - 1) umma_commit(&acc_full[ab]);
                         }
-                        umma_commit(&b_empty[s]);                    // stage may be refilled
-                        if (u == TC_NU - 1) umma_commit(&a_empty[kb]);  // A block free for the next tile
+                        __syncwarp();
                     }
-                    umma_commit(&acc_full[ab]);
                 }
             }
         }
@@ -336,7 +345,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer: the other input's halo chunks =====================
-        if (lane == 0) {
+        {
             uint32_t bcount = 0;
             const uint64_t pol = l2_policy_evict_last();
             auto load = [&](void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -350,17 +359,23 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                     for (int j = 0; j < ncb; ++j, ++bcount) {
                         const int s = bcount % TB_NBST;
                         mbar_wait(&b_empty[s], ((bcount / TB_NBST) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&b_full[s], 2 * TC_BBLK);
-                        load(sB + (s * 2 + 0) * TC_BBLK, &moh, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
-                                    T.yc0 - TC_DR + u * TC_UR, img);
-                        load(sB + (s * 2 + 1) * TC_BBLK, &mol, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
-                                    T.yc0 - TC_DR + u * TC_UR, img);
+                        if (elect_one_sync()) {
+                            mbar_arrive_expect_tx(&b_full[s], 2 * TC_BBLK);
+                            load(sB + (s * 2 + 0) * TC_BBLK, &moh, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
+                                 T.yc0 - TC_DR + u * TC_UR, img);
+                            load(sB + (s * 2 + 1) * TC_BBLK, &mol, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
+                                 T.yc0 - TC_DR + u * TC_UR, img);
+                        }
+                        __syncwarp();
                     }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp runs the control flow (converged); one elected lane issues the MMAs and
+        // commits.  (Issuing from `if (lane == 0)` made nvcc wrap every UTCHMMA in an
+        // ELECT / BRA.U.ANY per-active-lane loop: ~70 cycles per MMA, measured.)
+        {
             const uint32_t idesc = umma_idesc_bf16_f32(128, TC_KB, 1);   // N = 64, B MN-major
             uint32_t bcount = 0, ucount = 0, tcount = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
@@ -369,7 +384,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                 tcgen05_fence_after();
                 for (int u = 0; u < TC_NU; ++u, ++ucount) {
                     const int as = ucount % TB_NAST;
-                    const bool rec = dbg && blockIdx.x == 0 && ucount < 64;
+                    const bool rec = dbg && blockIdx.x == 0 && ucount < 64 && lane == 0;
                     if (rec) dbg[ucount * 8 + 4] = clock64();
                     mbar_wait(&a_full[as], (ucount / TB_NAST) & 1);
                     if (rec) dbg[ucount * 8 + 5] = clock64();
@@ -379,24 +394,29 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                         const int s = bcount % TB_NBST;
                         mbar_wait(&b_full[s], (bcount / TB_NBST) & 1);
                         tcgen05_fence_after();
-                        const uint64_t bh = umma_desc_mn_sw128(smem_u32(sB + (s * 2 + 0) * TC_BBLK), TC_BBLK);
-                        const uint64_t bl = umma_desc_mn_sw128(smem_u32(sB + (s * 2 + 1) * TC_BBLK), TC_BBLK);
-                        const uint32_t d = tmem_base + ab * 256 + j * TC_KB;
+                        if (elect_one_sync()) {
+                            const uint64_t bh = umma_desc_mn_sw128(smem_u32(sB + (s * 2 + 0) * TC_BBLK), TC_BBLK);
+                            const uint64_t bl = umma_desc_mn_sw128(smem_u32(sB + (s * 2 + 1) * TC_BBLK), TC_BBLK);
+                            const uint64_t ah0 = umma_desc_k_sw32(a_hi), al0 = umma_desc_k_sw32(a_lo);
+                            const uint32_t d = tmem_base + ab * 256 + j * TC_KB;
 #pragma unroll
-                        for (int ks = 0; ks < TB_KS; ++ks) {
-                            const uint64_t ah = umma_desc_k_sw32(a_hi + ks * 4096);
-                            const uint64_t al = umma_desc_k_sw32(a_lo + ks * 4096);
-                            const uint64_t kadv = (uint64_t)((ks * 16 * 128) >> 4);
-                            umma_bf16_ss(d, ah, bh + kadv, idesc, (u | ks) != 0);
-                            umma_bf16_ss(d, ah, bl + kadv, idesc, 1);
-                            umma_bf16_ss(d, al, bh + kadv, idesc, 1);
+                            for (int ks = 0; ks < TB_KS; ++ks) {
+                                const uint64_t ah = ah0 + (uint64_t)((ks * 4096) >> 4);
+                                const uint64_t al = al0 + (uint64_t)((ks * 4096) >> 4);
+                                const uint64_t kadv = (uint64_t)((ks * 16 * 128) >> 4);
+                                umma_bf16_ss(d, ah, bh + kadv, idesc, (u | ks) != 0);
+                                umma_bf16_ss(d, ah, bl + kadv, idesc, 1);
+                                umma_bf16_ss(d, al, bh + kadv, idesc, 1);
+                            }
+                            umma_commit(&b_empty[s]);
+                            if (j == ncb - 1) umma_commit(&a_empty[as]);
                         }
-                        umma_commit(&b_empty[s]);
+                        __syncwarp();
                     }
-                    umma_commit(&a_empty[as]);
                     if (rec) dbg[ucount * 8 + 6] = clock64();
                 }
-                umma_commit(&acc_full[ab]);
+                if (elect_one_sync()) umma_commit(&acc_full[ab]);
+                __syncwarp();
             }
         }
     } else if (warp < 18) {

@@ -86,6 +86,18 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                      smem_u32(bar))
                  : "memory");
 }
+// true in exactly one lane of a fully converged warp (the lane the hardware elects)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
