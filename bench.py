@@ -477,13 +477,13 @@ def main():
             "frac_hbm_peak": round(value / world / peak, 4),
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(ach / peak, 4),
-                         "traffic": (843838464 if (args.impl == "ours" and dominant == "correlation_backward") else None),
+                         "traffic": (843030000 if (args.impl == "ours" and dominant == "correlation_backward") else None),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of corr_bwd_tc_kernel<1>, "
-                                           "one launch, ncu --set full (profiles/r1g_ncu_full_summary.csv)",
+                                           "one launch, ncu --set full (profiles/r1i_ncu_full_summary.csv)",
                          "peak_source": peak_src,
                          "launch_ms": round(launch_ms, 4),
                          "note": "tensor-core kernel (bf16 hi/lo split, 3 MMAs per product) bound by on-chip operand movement, "
-                                 "not HBM: tensor pipe 42 % active, DRAM at ~30 % of peak; see DESIGN.md 4.1",
+                                 "not HBM: tensor pipe 46 % active, DRAM at ~30 % of peak; see DESIGN.md 4.1",
                          "fp32_tflops": round((51.79e9 * 3) / ((per_f + per_b) * 1e-3) / 1e12, 2)},
             "kernels": {"forward_ms": round(per_f, 4), "backward_ms": round(per_b, 4),
                         "forward_GBps": round(fwd_b / per_f / 1e6, 1), "backward_GBps": round(bwd_b / per_b / 1e6, 1)},
