@@ -472,7 +472,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "Correlation(pad=20,k=1,md=20,s1=1,s2=2) fwd+bwd on fp32 [8,256,112,256] per GPU "
                                    "(BASELINE configs[1])", "per_gpu_batch": B, "global_batch": B * world,
-                       "l2": "inputs+outputs 1.28 GB per step >> 126 MB L2 (no flush needed)",
+                       "l2": "inputs+outputs 1.75 GB per step >> 126 MB L2 (no flush needed)",
                        "parallelism": "replicas x%d (weak, no data-path collective)" % world, "impl": name},
             "frac_hbm_peak": round(value / world / peak, 4),
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
