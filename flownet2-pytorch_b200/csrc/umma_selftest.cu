@@ -172,3 +172,74 @@ int umma_selftest2(const void *A, const void *Bt, float *D, int a_sw32, cudaStre
 }
 
 }  // namespace fn2
+
+// ------------------------------------------------------------------------------------------------
+// TMA feed micro-benchmark (tools/tma_feed.py): how fast can one SM pull halo-style boxes
+// (64 channels x bw x bh class pixels of a [img][Hc][Wc][C] bf16 tensor, SW128) when nothing consumes
+// them?  Persistent CTAs, `stages`-deep ring, `per_stage` boxes per stage, access pattern of the
+// correlation kernels (tiles of 8x16, 7 units, C/64 k-blocks).  Writes cycles and bytes per CTA.
+// ------------------------------------------------------------------------------------------------
+namespace fn2 {
+
+__global__ void __launch_bounds__(64, 1)
+tma_feed_kernel(const __grid_constant__ CUtensorMap map, long long *__restrict__ out, int C, int Hc, int Wc,
+                int nimg, int bw, int bh, int stages, int per_stage, int iters) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int box_bytes = bw * bh * 128;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)stages * per_stage * box_bytes);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < stages; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid >= 32) return;
+    const int nkb = C / 64, nxt = (Wc + 15) / 16, nyt = (Hc + 7) / 8;
+    const int ntiles = nimg * nxt * nyt;
+    long long t0 = 0, bytes = 0;
+    int issued = 0, waited = 0;
+    auto issue = [&](int n) {
+        // n-th stage of this CTA: tile, unit, k-block as the correlation kernels walk them
+        const int per_tile = 7 * nkb;
+        const int tile = (blockIdx.x + (n / per_tile) * gridDim.x) % ntiles;
+        const int u = (n % per_tile) / nkb, kb = n % nkb;
+        const int img = tile / (nxt * nyt), yc0 = ((tile / nxt) % nyt) * 8, xc0 = (tile % nxt) * 16;
+        const int s = n % stages;
+        if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&bars[s], (uint32_t)(per_stage * box_bytes));
+            for (int b = 0; b < per_stage; ++b)
+                tma_load_4d(smem + ((size_t)s * per_stage + b) * box_bytes, &map, &bars[s], kb * 64,
+                            xc0 - 10 + (b * bw) % 36, yc0 - 10 + u * 4, (img + b) % nimg);
+        }
+        __syncwarp();
+    };
+    for (; issued < stages && issued < iters; ++issued) issue(issued);
+    t0 = clock64();
+    for (; waited < iters; ++waited) {
+        mbar_wait(&bars[waited % stages], (waited / stages) & 1);
+        bytes += (long long)per_stage * box_bytes;
+        if (issued < iters) { issue(issued); ++issued; }
+    }
+    const long long t1 = clock64();
+    if (tid == 0) { out[2 * blockIdx.x] = t1 - t0; out[2 * blockIdx.x + 1] = bytes; }
+}
+
+int tma_feed_bench(const void *base, long long *out, int nimg, int C, int Hc, int Wc, int bw, int bh, int stages,
+                   int per_stage, int iters, int grid, cudaStream_t st) {
+    CUtensorMap m;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wc, (uint64_t)Hc, (uint64_t)nimg};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)Wc * C * 2, (uint64_t)Hc * Wc * C * 2};
+    uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bh, 1u};
+    int rc = make_tensor_map_bf16_sw128(&m, base, 4, dims, strides, box);
+    if (rc) return rc;
+    const int smem = stages * per_stage * bw * bh * 128 + stages * 8 + 1024 + 64;
+    if (smem > 232448) return fail(FN2B200_EINVAL, "tma_feed_bench: %d bytes of shared memory requested", smem);
+    cudaError_t e = cudaFuncSetAttribute(tma_feed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail((int)e, "tma_feed_bench: smem attribute (%s)", cudaGetErrorString(e));
+    tma_feed_kernel<<<grid, 64, smem, st>>>(m, out, C, Hc, Wc, nimg, bw, bh, stages, per_stage, iters);
+    count_launch();
+    return check_launch("tma_feed_bench");
+}
+
+}  // namespace fn2
