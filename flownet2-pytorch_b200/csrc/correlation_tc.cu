@@ -329,7 +329,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
 
     if (tid == 0) {
         prefetch_tensormap(&moh); prefetch_tensormap(&mol);
-        for (int i = 0; i < TB_NAST; ++i) { mbar_init(&a_full[i], 512); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < TB_NAST; ++i) { mbar_init(&a_full[i], 16); mbar_init(&a_empty[i], 1); }   // one arrival per builder warp
         for (int i = 0; i < TB_MAXBST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < TB_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_barrier_init();
@@ -497,7 +497,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                 }
                 fence_proxy_async();          // generic-proxy writes -> visible to the tensor core
                 if (rec) dbg[ucount * 8 + 2] = clock64();
-                mbar_arrive(&a_full[as]);
+                __syncwarp();                 // every lane's stores + fence precede the warp's single arrival
+                if (lane == 0) mbar_arrive(&a_full[as]);
                 if (rec) dbg[ucount * 8 + 3] = clock64();
             }
         }
