@@ -286,7 +286,7 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 //       no-swizzle layout made the 2-byte band scatter 4-way bank conflicted: 70 % of wavefronts);
 //   B = the other input's halo chunk from the prepass copy ([pixel][channel] bf16 = MN-major operand),
 //       one 64-channel block per TMA stage;
-//   3 MMAs (hi*hi, hi*lo, lo*hi) per k-step, N = 64 per instruction.
+//   3 MMAs (hi*hi, hi*lo, lo*hi) per k-step, N = 128 per instruction (pairs of channel blocks).
 // Roles (704 threads): warp 0 TMA, warp 1 MMA, warps 2-17 builders, warps 18-21 epilogue.
 // Builders: FOUR threads per tile pixel = (halo-row pair) x (displacement half); a single warp per
 // scheduler ran ~2000 dependent instructions per unit at IPC ~0.2 and made the builder -- not the
@@ -297,12 +297,22 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 constexpr int TB_KS = TC_N / 16;                   // 9 k-steps per unit
 constexpr int TB_AHL = TB_KS * 4096;               // 36864 B: one of {hi, lo} of a unit's A
 constexpr int TB_ASTG = 2 * TB_AHL;                // 73728 B per A stage
-constexpr int TB_NAST = 2, TB_MAXBST = 4, TB_NACC = 2;
+constexpr int TB_NAST = 2, TB_MAXBST = 6, TB_NACC = 2;
 constexpr int TB_SMEM_A = TB_NAST * TB_ASTG;       // 147456
 constexpr int TB_NBAR = 2 * TB_NAST + 2 * TB_MAXBST + 2 * TB_NACC;
+// B staging: the unit's 144 K indices in 3 groups of 48 (12 halo columns x 4 rows); one stage = one
+// group x one PAIR of 64-channel blocks, hi and lo = 4 boxes of 6 KB.  MMAs then cover N = 128 columns:
+// an N = 64 MMA re-reads the 4-KB A slice for 2 KB of B and the tensor pipe ran at ~65 cycles per
+// 32-cycle MMA (clock64 timeline); N = 256 stages do not fit next to the double-buffered A.
+constexpr int TB_NG = 3, TB_GW = TC_HW / TB_NG, TB_GK = TC_UR * TB_GW;   // 3 groups, 12 columns, 48 K
+constexpr int TB_GBLK = TB_GK * 128;               // 6144 B: one 64-channel block of a group's rows
+constexpr int TB_BSTAGE = 4 * TB_GBLK;             // 24576 B: [hi|lo][2 channel blocks][48 rows x 128 B]
+__host__ __device__ constexpr uint32_t tb_kindex(uint32_t hrl, uint32_t qx) {
+    return (qx / TB_GW) * TB_GK + hrl * TB_GW + (qx % TB_GW);
+}
 constexpr int TB_THREADS = 704;                    // warp 0 TMA, 1 MMA, 2-17 builders, 18-21 epilogue
 __host__ __device__ constexpr int tb_smem_bytes(int bst) {
-    return TB_SMEM_A + bst * 2 * TC_BBLK + TB_NBAR * 8 + 16 + 1024;
+    return TB_SMEM_A + bst * TB_BSTAGE + TB_NBAR * 8 + 16 + 1024;
 }
 
 
@@ -314,8 +324,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sA = smem;                          // [stage][hl][9 k-steps][2 chunks][16 groups][8 x 16 B]
-    unsigned char *sB = smem + TB_SMEM_A;              // [stage][hl][144 rows x 128 B] (SW128)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TB_NBST * 2 * TC_BBLK);
+    unsigned char *sB = smem + TB_SMEM_A;              // [stage][hl][2 channel blocks][48 rows x 128 B] (SW128, MN-major)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TB_NBST * TB_BSTAGE);
     uint64_t *a_full = bars, *a_empty = a_full + TB_NAST;
     uint64_t *b_full = a_empty + TB_NAST, *b_empty = b_full + TB_MAXBST;
     uint64_t *acc_full = b_empty + TB_MAXBST, *acc_empty = acc_full + TB_NACC;
@@ -356,18 +366,23 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                 const TcTile T = tc_decode(t, nxt, nyt);
                 const int img = T.n * 4 + T.py * 2 + T.px;
                 for (int u = 0; u < TC_NU; ++u)
-                    for (int j = 0; j < ncb; ++j, ++bcount) {
-                        const int s = bcount % TB_NBST;
-                        mbar_wait(&b_empty[s], ((bcount / TB_NBST) & 1) ^ 1);
-                        if (elect_one_sync()) {
-                            mbar_arrive_expect_tx(&b_full[s], 2 * TC_BBLK);
-                            load(sB + (s * 2 + 0) * TC_BBLK, &moh, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
-                                 T.yc0 - TC_DR + u * TC_UR, img);
-                            load(sB + (s * 2 + 1) * TC_BBLK, &mol, &b_full[s], j * TC_KB, T.xc0 - TC_DR,
-                                 T.yc0 - TC_DR + u * TC_UR, img);
+                    for (int g = 0; g < TB_NG; ++g)
+                        for (int jp = 0; jp < ncb; jp += 2, ++bcount) {
+                            const int s = bcount % TB_NBST;
+                            const int nb = (ncb - jp) < 2 ? 1 : 2;     // channel blocks in this stage
+                            mbar_wait(&b_empty[s], ((bcount / TB_NBST) & 1) ^ 1);
+                            if (elect_one_sync()) {
+                                mbar_arrive_expect_tx(&b_full[s], (uint32_t)(2 * nb * TB_GBLK));
+                                unsigned char *dst = sB + s * TB_BSTAGE;
+                                for (int j = 0; j < nb; ++j) {
+                                    load(dst + j * TB_GBLK, &moh, &b_full[s], (jp + j) * TC_KB, T.xc0 - TC_DR + g * TB_GW,
+                                         T.yc0 - TC_DR + u * TC_UR, img);
+                                    load(dst + (2 + j) * TB_GBLK, &mol, &b_full[s], (jp + j) * TC_KB, T.xc0 - TC_DR + g * TB_GW,
+                                         T.yc0 - TC_DR + u * TC_UR, img);
+                                }
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
-                    }
             }
         }
     } else if (warp == 1) {
@@ -376,7 +391,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
         // commits.  (Issuing from `if (lane == 0)` made nvcc wrap every UTCHMMA in an
         // ELECT / BRA.U.ANY per-active-lane loop: ~70 cycles per MMA, measured.)
         {
-            const uint32_t idesc = umma_idesc_bf16_f32(128, TC_KB, 1);   // N = 64, B MN-major
+            const uint32_t idesc2 = umma_idesc_bf16_f32(128, 2 * TC_KB, 1);   // N = 128, B MN-major
+            const uint32_t idesc1 = umma_idesc_bf16_f32(128, TC_KB, 1);       // N = 64 (odd last channel block)
             uint32_t bcount = 0, ucount = 0, tcount = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
                 const int ab = tcount % TB_NACC;
@@ -390,29 +406,31 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                     if (rec) dbg[ucount * 8 + 5] = clock64();
                     tcgen05_fence_after();
                     const uint32_t a_hi = smem_u32(sA + as * TB_ASTG), a_lo = a_hi + TB_AHL;
-                    for (int j = 0; j < ncb; ++j, ++bcount) {
-                        const int s = bcount % TB_NBST;
-                        mbar_wait(&b_full[s], (bcount / TB_NBST) & 1);
-                        tcgen05_fence_after();
-                        if (elect_one_sync()) {
-                            const uint64_t bh = umma_desc_mn_sw128(smem_u32(sB + (s * 2 + 0) * TC_BBLK), TC_BBLK);
-                            const uint64_t bl = umma_desc_mn_sw128(smem_u32(sB + (s * 2 + 1) * TC_BBLK), TC_BBLK);
-                            const uint64_t ah0 = umma_desc_k_sw32(a_hi), al0 = umma_desc_k_sw32(a_lo);
-                            const uint32_t d = tmem_base + ab * 256 + j * TC_KB;
+                    for (int g = 0; g < TB_NG; ++g)
+                        for (int jp = 0; jp < ncb; jp += 2, ++bcount) {
+                            const int s = bcount % TB_NBST;
+                            mbar_wait(&b_full[s], (bcount / TB_NBST) & 1);
+                            tcgen05_fence_after();
+                            if (elect_one_sync()) {
+                                const uint32_t idesc = (ncb - jp) < 2 ? idesc1 : idesc2;
+                                const uint32_t bbase = smem_u32(sB + s * TB_BSTAGE);
+                                const uint64_t bh = umma_desc_mn_sw128(bbase, TB_GBLK);
+                                const uint64_t bl = umma_desc_mn_sw128(bbase + 2 * TB_GBLK, TB_GBLK);
+                                const uint32_t d = tmem_base + ab * 256 + jp * TC_KB;
 #pragma unroll
-                            for (int ks = 0; ks < TB_KS; ++ks) {
-                                const uint64_t ah = ah0 + (uint64_t)((ks * 4096) >> 4);
-                                const uint64_t al = al0 + (uint64_t)((ks * 4096) >> 4);
-                                const uint64_t kadv = (uint64_t)((ks * 16 * 128) >> 4);
-                                umma_bf16_ss(d, ah, bh + kadv, idesc, (u | ks) != 0);
-                                umma_bf16_ss(d, ah, bl + kadv, idesc, 1);
-                                umma_bf16_ss(d, al, bh + kadv, idesc, 1);
+                                for (int ks = 0; ks < TB_GK / 16; ++ks) {
+                                    const uint64_t ah = umma_desc_k_sw32(a_hi + (g * 3 + ks) * 4096);
+                                    const uint64_t al = umma_desc_k_sw32(a_lo + (g * 3 + ks) * 4096);
+                                    const uint64_t kadv = (uint64_t)((ks * 16 * 128) >> 4);
+                                    umma_bf16_ss(d, ah, bh + kadv, idesc, (u | g | ks) != 0);
+                                    umma_bf16_ss(d, ah, bl + kadv, idesc, 1);
+                                    umma_bf16_ss(d, al, bh + kadv, idesc, 1);
+                                }
+                                umma_commit(&b_empty[s]);
+                                if (g == TB_NG - 1 && jp + 2 >= ncb) umma_commit(&a_empty[as]);
                             }
-                            umma_commit(&b_empty[s]);
-                            if (j == ncb - 1) umma_commit(&a_empty[as]);
+                            __syncwarp();
                         }
-                        __syncwarp();
-                    }
                     if (rec) dbg[ucount * 8 + 6] = clock64();
                 }
                 if (elect_one_sync()) umma_commit(&acc_full[ab]);
@@ -435,7 +453,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
             uint32_t two = 0;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                const uint32_t k = (2 * hp + hh) * TC_HW + px_t + j0 + jj;
+                const uint32_t k = tb_kindex(2 * hp + hh, px_t + j0 + jj);
                 const uint32_t off = (k >> 4) * 4096 + p * 32 + ((((k >> 3) & 1) ^ swz) << 4) + (k & 7) * 2;
                 two |= off << (16 * hh);
             }
@@ -621,8 +639,8 @@ static int launch_bwd_tc(const __nv_bfloat16 *oh, const __nv_bfloat16 *ol, const
                          const CorrParams &p, cudaStream_t st) {
     CUtensorMap moh, mol;
     int rc;
-    if ((rc = make_class_map(&moh, oh, p, TC_HW, TC_UR))) return rc;
-    if ((rc = make_class_map(&mol, ol, p, TC_HW, TC_UR))) return rc;
+    if ((rc = make_class_map(&moh, oh, p, TB_GW, TC_UR))) return rc;     // one K group: 12 halo columns x 4 rows
+    if ((rc = make_class_map(&mol, ol, p, TB_GW, TC_UR))) return rc;
     const int Hc = p.H / 2, Wc = p.W / 2;
     const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
     const int ntiles = p.B * 4 * nxt * nyt;
