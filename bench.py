@@ -460,6 +460,8 @@ def main():
     if rank == 0:
         per_f, per_b = ms_f / K, ms_b / K
         dominant = "correlation_backward" if per_b >= per_f else "correlation_forward"
+        kname = {"correlation_backward": "corr_bwd_tc_kernel<WHICH> (one launch per input gradient)",
+                 "correlation_forward": "corr_tc_split_kernel + corr_fwd_tc_kernel"}[dominant] if args.impl == "ours" else dominant
         if dominant == "correlation_backward":
             launch_ms = per_b / (2 if args.impl == "ours" else 1)
             ach = (bwd_launch_b if args.impl == "ours" else bwd_b) / (launch_ms * 1e-3) / 1e9
@@ -475,7 +477,7 @@ def main():
                        "l2": "inputs+outputs 1.75 GB per step >> 126 MB L2 (no flush needed)",
                        "parallelism": "replicas x%d (weak, no data-path collective)" % world, "impl": name},
             "frac_hbm_peak": round(value / world / peak, 4),
-            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(ach / peak, 4),
                          "traffic": (843030000 if (args.impl == "ours" and dominant == "correlation_backward") else None),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of corr_bwd_tc_kernel<1>, "
