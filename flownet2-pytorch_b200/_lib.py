@@ -52,6 +52,10 @@ def _load():
     lib.fn2b200_resample2d_backward.argtypes = [_c_ptr, lp, _c_ptr, _c_ptr, _c_ptr, _c_ptr] + [_c_int] * 9 + [_c_ptr]
     lib.fn2b200_channelnorm_forward.argtypes = [_c_ptr, _c_ptr] + [_c_int] * 5 + [_c_ptr]
     lib.fn2b200_channelnorm_backward.argtypes = [_c_ptr] * 4 + [_c_int] * 5 + [_c_ptr]
+    lib.fn2b200_channelnorm_forward_16.argtypes = [_c_ptr, _c_ptr] + [_c_int] * 6 + [_c_ptr]
+    lib.fn2b200_channelnorm_forward_16.restype = _c_int
+    lib.fn2b200_channelnorm_backward_16.argtypes = [_c_ptr] * 4 + [_c_int] * 6 + [_c_ptr]
+    lib.fn2b200_channelnorm_backward_16.restype = _c_int
     lib.fn2b200_debug_umma_gemm.argtypes = [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr]
     lib.fn2b200_debug_umma_gemm.restype = _c_int
     lib.fn2b200_debug_tma_feed.argtypes = [_c_ptr, _c_ptr] + [_c_int] * 10 + [_c_ptr]
@@ -74,6 +78,7 @@ SYMBOLS = (
     "fn2b200_correlation_backward_workspace", "fn2b200_correlation_backward_ws",
     "fn2b200_resample2d_forward", "fn2b200_resample2d_backward",
     "fn2b200_channelnorm_forward", "fn2b200_channelnorm_backward",
+    "fn2b200_channelnorm_forward_16", "fn2b200_channelnorm_backward_16",
     "fn2b200_debug_umma_gemm", "fn2b200_debug_tma_feed",
 )
 

@@ -364,4 +364,28 @@ int fn2b200_channelnorm_backward(const float *in, const float *out, const float 
     return channelnorm_backward(in, out, gout, gin, B, C, H, W, (cudaStream_t)stream);
 }
 
+int fn2b200_channelnorm_forward_16(const void *in, void *out, int B, int C, int H, int W, int norm_deg,
+                                   int dtype, void *stream) {
+    (void)norm_deg;
+    if (B < 0 || C <= 0 || H <= 0 || W <= 0 || (dtype != 1 && dtype != 2))
+        return fail(FN2B200_EINVAL, "channelnorm_forward_16: bad shape [%d,%d,%d,%d] or dtype %d", B, C, H, W, dtype);
+    if ((int64_t)B * C * H * W >= (1LL << 31)) return fail(FN2B200_EINVAL, "channelnorm_forward_16: tensor too large");
+    if (B == 0) return 0;
+    if (!in || !out) return fail(FN2B200_ENULL, "channelnorm_forward_16: null pointer");
+    if (int rc = bind_device_of(in)) return rc;
+    return channelnorm_forward_half(in, out, B, C, H, W, dtype, (cudaStream_t)stream);
+}
+
+int fn2b200_channelnorm_backward_16(const void *in, const void *out, const void *gout, void *gin, int B, int C,
+                                    int H, int W, int norm_deg, int dtype, void *stream) {
+    (void)norm_deg;
+    if (B < 0 || C <= 0 || H <= 0 || W <= 0 || (dtype != 1 && dtype != 2))
+        return fail(FN2B200_EINVAL, "channelnorm_backward_16: bad shape [%d,%d,%d,%d] or dtype %d", B, C, H, W, dtype);
+    if ((int64_t)B * C * H * W >= (1LL << 31)) return fail(FN2B200_EINVAL, "channelnorm_backward_16: tensor too large");
+    if (B == 0) return 0;
+    if (!in || !out || !gout || !gin) return fail(FN2B200_ENULL, "channelnorm_backward_16: null pointer");
+    if (int rc = bind_device_of(in)) return rc;
+    return channelnorm_backward_half(in, out, gout, gin, B, C, H, W, dtype, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -9,6 +9,8 @@
 // then one 128-bit store.  No shared memory, no pre-zeroed outputs (the reference zero-fills
 // them first, channelnorm.py:11,23: 2x the write traffic).
 #include "common.cuh"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace fn2 {
 
@@ -105,6 +107,103 @@ channelnorm_bwd_scalar(const float *__restrict__ in, const float *__restrict__ o
         long i = ((long)b * C + c) * hw + p;
         gin[i] = cn_bwd(g, __ldg(in + i), o);
     }
+}
+
+// ---- 16-bit storage variants (the reference dispatches K8/K9 on half too, channelnorm_kernel.cu:111,152:
+// ChannelNorm is the one custom layer that sees fp16 tensors in --fp16 mode, models.py:39).  Same
+// arithmetic as the reference: square in the storage type's value, accumulate / divide in fp32, round once.
+template <typename T> __device__ __forceinline__ float h2f(T v);
+template <> __device__ __forceinline__ float h2f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float h2f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T f2h(float v);
+template <> __device__ __forceinline__ __half f2h<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 f2h<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// one thread = 8 consecutive pixels (one 128-bit load per channel)
+template <typename T>
+__global__ void __launch_bounds__(256)
+channelnorm_fwd_h8(const T *__restrict__ in, T *__restrict__ out, int C, int hw8, long n8) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n8) return;
+    int b = (int)(idx / hw8);
+    int p = (int)(idx - (long)b * hw8);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+        uint4 raw = *reinterpret_cast<const uint4 *>(in + (((long)b * C + c) * hw8 + p) * 8);
+        const T *v = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float x = h2f<T>(v[i]);
+            acc[i] += x * x;
+        }
+    }
+    uint4 o;
+    T *ov = reinterpret_cast<T *>(&o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ov[i] = f2h<T>(sqrtf(acc[i]));
+    *reinterpret_cast<uint4 *>(out + idx * 8) = o;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+channelnorm_fwd_h1(const T *__restrict__ in, T *__restrict__ out, int C, int hw, long n) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    int b = (int)(idx / hw);
+    int p = (int)(idx - (long)b * hw);
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) {
+        float x = h2f<T>(in[((long)b * C + c) * hw + p]);
+        acc += x * x;
+    }
+    out[idx] = f2h<T>(sqrtf(acc));
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+channelnorm_bwd_h1(const T *__restrict__ in, const T *__restrict__ out, const T *__restrict__ gout,
+                   T *__restrict__ gin, int C, int hw, long n) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    int b = (int)(idx / hw);
+    int p = (int)(idx - (long)b * hw);
+    float o = h2f<T>(out[idx]), g = h2f<T>(gout[idx]);
+    for (int c = 0; c < C; ++c) {
+        long i = ((long)b * C + c) * hw + p;
+        gin[i] = f2h<T>(cn_bwd(g, h2f<T>(in[i]), o));
+    }
+}
+
+template <typename T>
+static int channelnorm_forward_16(const void *in, void *out, int B, int C, int H, int W, cudaStream_t st) {
+    const int hw = H * W, Tn = 256;
+    if (hw % 8 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        long n8 = (long)B * (hw / 8);
+        channelnorm_fwd_h8<T><<<(unsigned)((n8 + Tn - 1) / Tn), Tn, 0, st>>>((const T *)in, (T *)out, C, hw / 8, n8);
+    } else {
+        long n = (long)B * hw;
+        channelnorm_fwd_h1<T><<<(unsigned)((n + Tn - 1) / Tn), Tn, 0, st>>>((const T *)in, (T *)out, C, hw, n);
+    }
+    count_launch();
+    return check_launch("channelnorm_forward(16-bit)");
+}
+template <typename T>
+static int channelnorm_backward_16(const void *in, const void *out, const void *gout, void *gin, int B, int C,
+                                   int H, int W, cudaStream_t st) {
+    const int hw = H * W, Tn = 256;
+    long n = (long)B * hw;
+    channelnorm_bwd_h1<T><<<(unsigned)((n + Tn - 1) / Tn), Tn, 0, st>>>((const T *)in, (const T *)out, (const T *)gout,
+                                                                        (T *)gin, C, hw, n);
+    count_launch();
+    return check_launch("channelnorm_backward(16-bit)");
+}
+// dtype: 1 = fp16, 2 = bf16
+int channelnorm_forward_half(const void *in, void *out, int B, int C, int H, int W, int dtype, cudaStream_t st) {
+    return dtype == 1 ? channelnorm_forward_16<__half>(in, out, B, C, H, W, st)
+                      : channelnorm_forward_16<__nv_bfloat16>(in, out, B, C, H, W, st);
+}
+int channelnorm_backward_half(const void *in, const void *out, const void *gout, void *gin, int B, int C, int H,
+                              int W, int dtype, cudaStream_t st) {
+    return dtype == 1 ? channelnorm_backward_16<__half>(in, out, gout, gin, B, C, H, W, st)
+                      : channelnorm_backward_16<__nv_bfloat16>(in, out, gout, gin, B, C, H, W, st);
 }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

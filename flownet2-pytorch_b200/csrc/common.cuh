@@ -111,6 +111,9 @@ __device__ __forceinline__ void red_add_f32(float *p, float v) {
 int channelnorm_forward(const float *in, float *out, int B, int C, int H, int W, cudaStream_t st);
 int channelnorm_backward(const float *in, const float *out, const float *gout, float *gin, int B,
                          int C, int H, int W, cudaStream_t st);
+int channelnorm_forward_half(const void *in, void *out, int B, int C, int H, int W, int dtype, cudaStream_t st);
+int channelnorm_backward_half(const void *in, const void *out, const void *gout, void *gin, int B, int C, int H,
+                              int W, int dtype, cudaStream_t st);
 int resample2d_forward(const float *img, const int64_t *istride, const float *flow, float *out,
                        int B, int C, int iH, int iW, int H, int W, int bilinear, cudaStream_t st);
 int resample2d_backward(const float *img, const int64_t *istride, const float *flow,

@@ -169,10 +169,22 @@ def resample2d_backward(input1, input2, grad_output, kernel_size=1, bilinear=Tru
     return g1, g2
 
 
+_DT16 = {torch.float16: 1, torch.bfloat16: 2}
+
+
 def channelnorm_forward(input1, norm_deg=2, out=None):
     _require_cuda(input1)
     if input1.dim() != 4:
         raise ValueError("channelnorm: expected a 4-D tensor, got %s" % (tuple(input1.shape),))
+    if input1.dtype in _DT16:        # native 16-bit kernels (the reference dispatches K8/K9 on half too)
+        a = input1 if input1.is_contiguous() else input1.contiguous()
+        B, C, H, W = a.shape
+        with torch.cuda.device_of(a):
+            if out is None:
+                out = torch.empty((B, 1, H, W), dtype=a.dtype, device=a.device)
+            check(LIB.fn2b200_channelnorm_forward_16(_ptr(a), _ptr(out), B, C, H, W, int(norm_deg), _DT16[a.dtype],
+                                                     _stream(a)), "channelnorm_forward")
+        return out
     a = _f32c(input1)
     B, C, H, W = a.shape
     with torch.cuda.device_of(a):
@@ -185,6 +197,15 @@ def channelnorm_forward(input1, norm_deg=2, out=None):
 
 def channelnorm_backward(input1, output, grad_output, norm_deg=2, out=None):
     _require_cuda(input1, output, grad_output)
+    if input1.dtype in _DT16 and output.dtype == input1.dtype and grad_output.dtype == input1.dtype:
+        a, o, g = (t if t.is_contiguous() else t.contiguous() for t in (input1, output, grad_output))
+        B, C, H, W = a.shape
+        with torch.cuda.device_of(a):
+            if out is None:
+                out = torch.empty_like(a)
+            check(LIB.fn2b200_channelnorm_backward_16(_ptr(a), _ptr(o), _ptr(g), _ptr(out), B, C, H, W, int(norm_deg),
+                                                      _DT16[a.dtype], _stream(a)), "channelnorm_backward")
+        return out
     a, o, g = _f32c(input1), _f32c(output), _f32c(grad_output)
     B, C, H, W = a.shape
     with torch.cuda.device_of(a):

@@ -141,6 +141,17 @@ int fn2b200_channelnorm_backward(const float *input1, const float *output,
                                  int H, int W, int norm_deg, void *stream);
 
 /*
+ * 16-bit storage variants of ChannelNorm (dtype: 1 = fp16, 2 = bf16; tensors of that type, fp32
+ * arithmetic inside).  The reference dispatches these kernels on half as well
+ * (channelnorm_kernel.cu:111,152); ChannelNorm is the one custom layer fed fp16 in --fp16 mode.
+ */
+int fn2b200_channelnorm_forward_16(const void *input1, void *output, int B, int C, int H, int W, int norm_deg,
+                                   int dtype, void *stream);
+int fn2b200_channelnorm_backward_16(const void *input1, const void *output, const void *grad_output,
+                                    void *grad_input1, int B, int C, int H, int W, int norm_deg, int dtype,
+                                    void *stream);
+
+/*
  * Introspection for benchmarks/tests: which kernel family the correlation entry points would
  * dispatch to for these parameters.  0 = generic gather kernels, 1 = TMA-tiled FMA kernels,
  * 2 = forward on tensor cores (when a workspace is supplied) + TMA-tiled FMA backward.
