@@ -481,7 +481,7 @@ def main():
                          "frac": round(ach / peak, 4),
                          "traffic": (843030000 if (args.impl == "ours" and dominant == "correlation_backward") else None),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of corr_bwd_tc_kernel<1>, "
-                                           "one launch, ncu --set full (profiles/r1i_ncu_full_summary.csv)",
+                                           "one launch, ncu --set full (profiles/r1j_ncu_full_summary.csv)",
                          "peak_source": peak_src,
                          "launch_ms": round(launch_ms, 4),
                          "note": "tensor-core kernel (bf16 hi/lo split, 3 MMAs per product) bound by on-chip operand movement, "
