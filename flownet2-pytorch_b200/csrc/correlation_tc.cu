@@ -295,7 +295,12 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 // columns of A are written ONCE at kernel start and the scatter offsets live in registers.
 // ------------------------------------------------------------------------------------------------
 constexpr int TB_KS = TC_N / 16;                   // 9 k-steps per unit
-constexpr int TB_AHL = TB_KS * 4096;               // 36864 B: one of {hi, lo} of a unit's A
+constexpr int TB_AMB = TC_N * 128;                 // 18432 B: one 64-pixel block of A, [k][64 pixels] (MN-major, SW128)
+constexpr int TB_AHL = 2 * TB_AMB;                 // 36864 B: one of {hi, lo} of a unit's A
+// byte offset of A element (tile pixel p, k): pixels contiguous, 16-byte chunk index XOR (k & 7)
+__host__ __device__ constexpr uint32_t tb_a_offset(uint32_t p, uint32_t k) {
+    return (p >> 6) * TB_AMB + k * 128u + (((((p & 63u) >> 3) ^ (k & 7u))) << 4) + (p & 7u) * 2u;
+}
 constexpr int TB_ASTG = 2 * TB_AHL;                // 73728 B per A stage
 constexpr int TB_NAST = 2, TB_MAXBST = 6, TB_NACC = 2;
 constexpr int TB_SMEM_A = TB_NAST * TB_ASTG;       // 147456
@@ -391,8 +396,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
         // commits.  (Issuing from `if (lane == 0)` made nvcc wrap every UTCHMMA in an
         // ELECT / BRA.U.ANY per-active-lane loop: ~70 cycles per MMA, measured.)
         {
-            const uint32_t idesc2 = umma_idesc_bf16_f32(128, 2 * TC_KB, 1);   // N = 128, B MN-major
-            const uint32_t idesc1 = umma_idesc_bf16_f32(128, TC_KB, 1);       // N = 64 (odd last channel block)
+            const uint32_t idesc2 = umma_idesc_bf16_f32(128, 2 * TC_KB, 1, 1);   // N = 128, A and B MN-major
+            const uint32_t idesc1 = umma_idesc_bf16_f32(128, TC_KB, 1, 1);       // N = 64 (odd last channel block)
             uint32_t bcount = 0, ucount = 0, tcount = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
                 const int ab = tcount % TB_NACC;
@@ -419,8 +424,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                                 const uint32_t d = tmem_base + ab * 256 + jp * TC_KB;
 #pragma unroll
                                 for (int ks = 0; ks < TB_GK / 16; ++ks) {
-                                    const uint64_t ah = umma_desc_k_sw32(a_hi + (g * 3 + ks) * 4096);
-                                    const uint64_t al = umma_desc_k_sw32(a_lo + (g * 3 + ks) * 4096);
+                                    const uint64_t ah = umma_desc_mn_sw128(a_hi + (g * TB_GK + ks * 16) * 128, TB_AMB);
+                                    const uint64_t al = umma_desc_mn_sw128(a_lo + (g * TB_GK + ks * 16) * 128, TB_AMB);
                                     const uint64_t kadv = (uint64_t)((ks * 16 * 128) >> 4);
                                     umma_bf16_ss(d, ah, bh + kadv, idesc, (u | g | ks) != 0);
                                     umma_bf16_ss(d, ah, bl + kadv, idesc, 1);
@@ -440,11 +445,14 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
     } else if (warp < 18) {
         // ===================== builders: banded gradOutput matrix A (hi / lo) =====================
         const int tb = tid - 64;                   // 0..511
-        const int p = tb & 127, sub = tb >> 7;     // tile pixel; sub-task (warp-uniform)
+        // A warp covers 4 tile rows x 8 pixels: with the MN-major SW128 layout its 32 two-byte stores of
+        // one (halo row, displacement) hit 32 different banks (the K-major layout cost 6.5 wavefronts
+        // per store, ncu r1j), and its loads are 4 rows x 64 B.
+        const int sub = tb >> 7, wq = (tb >> 5) & 3;                          // sub-task; tile quadrant (warp-uniform)
+        const int p = ((wq >> 1) * 4 + (lane >> 3)) * TC_TW + (wq & 1) * 8 + (lane & 7);   // tile pixel
         const int hp = sub >> 1, jh = sub & 1;     // halo rows {2hp, 2hp+1}; displacements [11*jh, 11*jh + nj)
         const int j0 = jh * 11, nj = jh ? 10 : 11;
         const int py_t = p >> 4, px_t = p & 15;
-        const uint32_t swz = (p >> 2) & 1;
         const int iplane = (int)plane;             // all tensors < 2^31 elements (checked by the C ABI)
         // scatter offsets (unit-invariant): entry (hh, jj) -> k = (2hp+hh)*36 + px_t + j0 + jj
         uint32_t offs[11];
@@ -454,8 +462,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const uint32_t k = tb_kindex(2 * hp + hh, px_t + j0 + jj);
-                const uint32_t off = (k >> 4) * 4096 + p * 32 + ((((k >> 3) & 1) ^ swz) << 4) + (k & 7) * 2;
-                two |= off << (16 * hh);
+                two |= tb_a_offset(p, k) << (16 * hh);
             }
             offs[jj] = two;
         }
@@ -465,33 +472,51 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
             const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
             const bool pix_ok = (yc < Hc) && (xc < Wc);
             const int nbase = T.n * (TC_DS * TC_DS);
+            // Per-tile address set-up (element offsets fit in 32 bits): for unit u the band row of halo
+            // row hrl = 2hp+hh starts at off[hh] + u * dstep; consecutive displacements are `step` apart.
+            int off[2], dstep, step, tj0[2], ys0[2];
+            uint32_t colmask = 0;                                  // WHICH == 2: source columns inside the image
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int hrl = 2 * hp + hh;
+                tj0[hh] = hrl - py_t;                              // tj + 10 at u = 0 (+4 per unit)
+                if (WHICH == 1) {
+                    ys0[hh] = 0;
+                    off[hh] = ((nbase + tj0[hh] * TC_DS + j0) * H + (2 * yc + T.py)) * W + (2 * xc + T.px);
+                } else {
+                    ys0[hh] = T.yc0 - TC_DR + hrl;                 // source pixel row at u = 0 (+4 per unit)
+                    const int xs0 = T.xc0 - TC_DR + px_t + j0;     // source column for jj = 0
+                    off[hh] = ((nbase + (TC_DS - 1 - tj0[hh]) * TC_DS + (TC_DS - 1 - j0)) * H + (2 * ys0[hh] + T.py)) * W +
+                              (2 * xs0 + T.px);
+                    if (hh == 0)
+#pragma unroll
+                        for (int jj = 0; jj < 11; ++jj)
+                            if ((unsigned)(xs0 + jj) < (unsigned)Wc) colmask |= 1u << jj;
+                }
+            }
+            if (WHICH == 1) {
+                step = iplane;                                     // next ti -> next plane
+                dstep = TC_UR * TC_DS * iplane;                    // next unit -> tj + 4
+            } else {
+                step = 2 - iplane;                                 // j -> j+1: -1 plane, +2 in x
+                dstep = -TC_UR * TC_DS * iplane + 2 * TC_UR * W;   // next unit: tj + 4 -> -84 planes; source row + 4 -> +8 rows
+                colmask &= (1u << nj) - 1u;
+            }
             for (int u = 0; u < TC_NU; ++u, ++ucount) {
                 const int as = ucount % TB_NAST;
+                // (1) issue this thread's 22 gradOutput loads before touching shared memory
                 float v[2][11];
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    const int hrl = 2 * hp + hh;
-                    const int tjp = u * TC_UR + hrl - py_t;       // tj + 10 of this (pixel row, halo row) pair
-                    bool row_ok = (tjp >= 0) && (tjp < TC_DS);
-                    int off0, step, xs0 = 0;
-                    if (WHICH == 1) {
-                        row_ok = row_ok && pix_ok;                // gO at the output pixel itself
-                        off0 = ((nbase + tjp * TC_DS + j0) * H + (2 * yc + T.py)) * W + (2 * xc + T.px);
-                        step = iplane;                            // next ti -> next plane
-                    } else {
-                        const int ycs = T.yc0 - TC_DR + u * TC_UR + hrl;   // source pixel row (class coords)
-                        row_ok = row_ok && (ycs >= 0) && (ycs < Hc);
-                        xs0 = T.xc0 - TC_DR + px_t + j0;                   // source column for jj = 0
-                        // plane (20 - tjp, 20 - j), pixel (ycs, xs0 + jj): j -> j+1 moves -1 plane, +2 in x
-                        off0 = ((nbase + (TC_DS - 1 - tjp) * TC_DS + (TC_DS - 1 - j0)) * H + (2 * ycs + T.py)) * W +
-                               (2 * xs0 + T.px);
-                        step = 2 - iplane;
-                    }
-                    if (!row_ok) off0 = 0;
+                    const int tjp = tj0[hh] + u * TC_UR;
+                    bool row_ok = (unsigned)tjp < (unsigned)TC_DS;
+                    if (WHICH == 1) row_ok = row_ok && pix_ok;
+                    else row_ok = row_ok && ((unsigned)(ys0[hh] + u * TC_UR) < (unsigned)Hc);
+                    const int base = off[hh] + u * dstep;      // only dereferenced under `ok`
 #pragma unroll
                     for (int jj = 0; jj < 11; ++jj) {
-                        const bool ok = row_ok && (jj < nj) && (WHICH == 1 || ((unsigned)(xs0 + jj) < (unsigned)Wc));
-                        v[hh][jj] = ok ? __ldg(gout + (off0 + jj * step)) : 0.f;
+                        const bool ok = row_ok && (WHICH == 1 ? (jj < nj) : ((colmask >> jj) & 1u));
+                        v[hh][jj] = ok ? __ldg(gout + (base + jj * step)) : 0.f;
                     }
                 }
                 const bool rec = dbg && blockIdx.x == 0 && tb == 0 && ucount < 64;
