@@ -115,7 +115,7 @@ int make_tensor_map_bf16_sw128(CUtensorMap *map, const void *base, int rank, con
 int umma_selftest(const void *A, const void *B, float *D, int K, cudaStream_t st);
 int umma_selftest2(const void *A, const void *Bt, float *D, int a_sw32, cudaStream_t st);
 int tma_feed_bench(const void *base, long long *out, int nimg, int C, int Hc, int Wc, int bw, int bh, int stages,
-                   int per_stage, int iters, int grid, cudaStream_t st);
+                   int per_stage, int iters, int grid, int cluster, int warps, cudaStream_t st);
 
 static int fill_corr_params(CorrParams &p, int B, int C, int H, int W, int pad, int k, int md,
                             int s1, int s2) {
@@ -163,11 +163,12 @@ extern "C" {
 int fn2b200_version(void) { return FN2B200_VERSION; }
 
 int fn2b200_debug_tma_feed(const void *base_bf16, long long *out, int nimg, int C, int Hc, int Wc, int box_w,
-                           int box_h, int stages, int boxes_per_stage, int iters, int grid, void *stream) {
+                           int box_h, int stages, int boxes_per_stage, int iters, int grid, int cluster, int producer_warps,
+                           void *stream) {
     if (!base_bf16 || !out) return fail(FN2B200_ENULL, "debug_tma_feed: null pointer");
     if (int rc = bind_device_of(out)) return rc;
     return tma_feed_bench(base_bf16, out, nimg, C, Hc, Wc, box_w, box_h, stages, boxes_per_stage, iters, grid,
-                          (cudaStream_t)stream);
+                          cluster, producer_warps, (cudaStream_t)stream);
 }
 
 int fn2b200_debug_umma_gemm(const void *A_bf16, const void *B_bf16, float *D, int K, void *stream) {

@@ -35,17 +35,15 @@ constexpr int TC_NU = TC_HH / TC_UR;           // 7 units per tile
 constexpr int TC_N = TC_UR * TC_HW;            // 144 accumulator columns per unit
 constexpr int TC_KB = 64;                      // channels per k-block (128 B of bf16)
 constexpr int TC_MAXKB = 4;                    // C <= 256
-constexpr int TC_MAXBST = 6;                   // B ring stages: as many as shared memory allows (runtime)
+constexpr int TC_MAXBST = 12;                  // B ring slots (one per hi / lo half-stage): as many as shared memory allows (runtime)
 constexpr int TC_NACC = 3;                     // TMEM accumulator buffers
 constexpr int TC_DS = 2 * TC_DR + 1;           // 21
 constexpr int TC_ABLK = 128 * 128;             // bytes of one A k-block (128 rows x 128 B)
 constexpr int TC_BBLK = TC_N * 128;            // bytes of one B k-block (144 rows x 128 B)
-constexpr int TC_EPITCH = TC_HW + 1;           // 37 floats per epilogue staging row
-constexpr int TC_SMEM_E = 128 * TC_EPITCH * 4;             // 18944
 constexpr int TC_NBAR = 2 * TC_MAXKB + 2 * TC_MAXBST + 2 * TC_NACC;
 constexpr int TC_SMEM_MAX = 232448;                        // 227 KB opt-in limit per CTA
 __host__ __device__ constexpr int tc_smem_bytes(int nkb, int bst) {
-    return 2 * nkb * TC_ABLK + bst * 2 * TC_BBLK + TC_SMEM_E + TC_NBAR * 8 + 16 + 1024;
+    return 2 * nkb * TC_ABLK + bst * TC_BBLK + TC_NBAR * 8 + 16 + 1024;   // bst slots of one box
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -118,20 +116,55 @@ __device__ __forceinline__ TcTile tc_decode(int t, int nxt, int nyt) {
     return r;
 }
 
-__global__ void __launch_bounds__(192, 1)
+// A CTA's work list: whole tiles tn, tn + grid, ... below `full`, then its share [w, w1) of the
+// (tile, unit) pairs of the last partial round (tile = full + w / 7).
+struct TcSeg {
+    int t, ua, ub;
+};
+__device__ __forceinline__ bool tc_next_seg(int &tn, int &w, int full, int w1, TcSeg &sg) {
+    if (tn < full) {
+        sg.t = tn; sg.ua = 0; sg.ub = TC_NU;
+        tn += gridDim.x;
+        return true;
+    }
+    if (w < w1) {
+        sg.t = full + w / TC_NU; sg.ua = w % TC_NU;
+        sg.ub = (TC_NU - sg.ua < w1 - w) ? TC_NU : sg.ua + (w1 - w);
+        w += sg.ub - sg.ua;
+        return true;
+    }
+    return false;
+}
+
+// One warp keeps only ONE batch of TMA boxes in flight whatever the ring depth (tools/tma_feed.py: 15 B/clk/SM
+// per warp with 18-KB batches, 28 with 36-KB ones, x2 / x4 with 2 / 4 issuing warps, ~75 B/clk/SM ceiling), so
+// the stages are dealt round-robin to `nprod` producer warps: warp 0 and warps 10...
+// Warps: 0 TMA, 1 MMA, 2-9 epilogue (two per TMEM lane quadrant, two halo rows of each unit each), 10.. TMA.
+constexpr int TC_MAXPROD = 4;
+constexpr int TC_EPIWARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPIWARPS + 32 * (TC_MAXPROD - 1);
+__global__ void __launch_bounds__(TC_THREADS, 1)
 corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ CUtensorMap m1l,
                    const __grid_constant__ CUtensorMap m2h, const __grid_constant__ CUtensorMap m2l,
-                   float *__restrict__ out, int B, int C, int H, int W, int ntiles, int TC_BST, int hint) {
+                   float *__restrict__ out, int B, int C, int H, int W, int ntiles, int TC_BST, int hint,
+                   int nprod, long long *__restrict__ dbg) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Hc = H >> 1, Wc = W >> 1;
     const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
     const int nkb = C / TC_KB;
+    // Whole tiles round-robin over the CTAs (neighbouring tiles run concurrently and share their halos in L2;
+    // contiguous per-CTA ranges were 50 % slower) for as many full rounds as there are; the tiles of the last,
+    // partial round are dealt out by (tile, unit) pairs -- the 7 units of a tile write disjoint displacement
+    // rows -- so that 1792 tiles on 148 SMs cost 12 rounds + one unit, not 13 rounds.
+    const int full = (ntiles / (int)gridDim.x) * (int)gridDim.x;
+    const int wtotal = (ntiles - full) * TC_NU, wper = (wtotal + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int w0 = (int)blockIdx.x * wper < wtotal ? (int)blockIdx.x * wper : wtotal;
+    const int w1 = (w0 + wper < wtotal) ? w0 + wper : wtotal;
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sA = smem;                                   // [hl][kb][128 x 128 B]
-    unsigned char *sB = smem + 2 * nkb * TC_ABLK;               // [stage][hl][144 x 128 B]
-    float *sE = reinterpret_cast<float *>(sB + TC_BST * 2 * TC_BBLK);   // [128][37]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(sE) + TC_SMEM_E);
+    unsigned char *sB = smem + 2 * nkb * TC_ABLK;               // [slot][144 x 128 B]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TC_BST * TC_BBLK);
     uint64_t *a_full = bars, *a_empty = bars + TC_MAXKB;
     uint64_t *b_full = bars + 2 * TC_MAXKB, *b_empty = b_full + TC_MAXBST;
     uint64_t *acc_full = b_empty + TC_MAXBST, *acc_empty = acc_full + TC_NACC;
@@ -142,7 +175,7 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
         prefetch_tensormap(&m2h); prefetch_tensormap(&m2l);
         for (int i = 0; i < TC_MAXKB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < TC_MAXBST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 32 * TC_EPIWARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -151,20 +184,24 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ===================== TMA producer (converged warp, one elected lane issues) =====================
-        {
-            uint32_t bcount = 0;
+    if (warp == 0 || warp >= 2 + TC_EPIWARPS) {
+        // ===================== TMA producers (converged warps, one elected lane issues) =====================
+        const int prod = warp == 0 ? 0 : warp - (1 + TC_EPIWARPS);
+        if (prod < nprod) {
+            uint32_t bcount = 0, job = 0;          // job: every A block / B stage in issue order
             int it = 0;
             const uint64_t pol = l2_policy_evict_last();
             auto load = [&](void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3) {
                 if (hint) tma_load_4d_hint(dst, m, bar, c0, c1, c2, c3, pol);
                 else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
             };
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                const TcTile T = tc_decode(t, nxt, nyt);
+            TcSeg sg;
+            for (int tn = blockIdx.x, w = w0; tc_next_seg(tn, w, full, w1, sg); ++it) {
+                const int ua = sg.ua, ub = sg.ub;
+                const TcTile T = tc_decode(sg.t, nxt, nyt);
                 const int img = T.n * 4 + T.py * 2 + T.px;
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = 0; kb < nkb; ++kb, ++job) {
+                    if ((int)(job % (uint32_t)nprod) != prod) continue;
                     mbar_wait(&a_empty[kb], (it & 1) ^ 1);
                     if (elect_one_sync()) {
                         mbar_arrive_expect_tx(&a_full[kb], 2 * TC_ABLK);
@@ -173,19 +210,20 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
                     }
                     __syncwarp();
                 }
-                for (int u = 0; u < TC_NU; ++u)
-                    for (int kb = 0; kb < nkb; ++kb, ++bcount) {
-                        const int s = bcount % TC_BST;
-                        mbar_wait(&b_empty[s], ((bcount / TC_BST) & 1) ^ 1);
-                        if (elect_one_sync()) {
-                            mbar_arrive_expect_tx(&b_full[s], 2 * TC_BBLK);
-                            load(sB + (s * 2 + 0) * TC_BBLK, &m2h, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
-                                 T.yc0 - TC_DR + u * TC_UR, img);
-                            load(sB + (s * 2 + 1) * TC_BBLK, &m2l, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
-                                 T.yc0 - TC_DR + u * TC_UR, img);
+                // B: one 18-KB box per half-stage (hi, then lo, of one unit x k-block) -- TC_BST slots
+                for (int u = ua; u < ub; ++u)
+                    for (int kb = 0; kb < nkb; ++kb)
+                        for (int hl = 0; hl < 2; ++hl, ++bcount, ++job) {
+                            if ((int)(job % (uint32_t)nprod) != prod) continue;
+                            const int s = bcount % TC_BST;
+                            mbar_wait(&b_empty[s], ((bcount / TC_BST) & 1) ^ 1);
+                            if (elect_one_sync()) {
+                                mbar_arrive_expect_tx(&b_full[s], TC_BBLK);
+                                load(sB + s * TC_BBLK, hl ? &m2l : &m2h, &b_full[s], kb * TC_KB, T.xc0 - TC_DR,
+                                     T.yc0 - TC_DR + u * TC_UR, img);
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
-                    }
             }
         }
     } else if (warp == 1) {
@@ -194,60 +232,88 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
             const uint32_t idesc = umma_idesc_bf16_f32(128, TC_N);
             uint32_t bcount = 0, acount = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                for (int u = 0; u < TC_NU; ++u, ++acount) {
+            TcSeg sg;
+            for (int tn = blockIdx.x, w = w0; tc_next_seg(tn, w, full, w1, sg); ++it) {
+                const int ua = sg.ua, ub = sg.ub;
+                for (int u = ua; u < ub; ++u, ++acount) {
                     const int ab = acount % TC_NACC;
+                    const bool rec = dbg && blockIdx.x == 0 && acount < 64 && lane == 0;
+                    long long bwait = 0;
+                    if (rec) dbg[acount * 8 + 0] = clock64();
                     mbar_wait(&acc_empty[ab], ((acount / TC_NACC) & 1) ^ 1);
+                    if (rec) dbg[acount * 8 + 1] = clock64();
                     tcgen05_fence_after();
                     const uint32_t d = tmem_base + ab * TC_N;
-                    for (int kb = 0; kb < nkb; ++kb, ++bcount) {
-                        if (u == 0) mbar_wait(&a_full[kb], it & 1);
-                        const int s = bcount % TC_BST;
-                        mbar_wait(&b_full[s], (bcount / TC_BST) & 1);
-                        tcgen05_fence_after();
-                        if (elect_one_sync()) {
-                            const uint64_t ah = umma_desc_k_sw128(smem_u32(sA + (0 * nkb + kb) * TC_ABLK));
-                            const uint64_t al = umma_desc_k_sw128(smem_u32(sA + (1 * nkb + kb) * TC_ABLK));
-                            const uint64_t bh = umma_desc_k_sw128(smem_u32(sB + (s * 2 + 0) * TC_BBLK));
-                            const uint64_t bl = umma_desc_k_sw128(smem_u32(sB + (s * 2 + 1) * TC_BBLK));
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (u == ua) mbar_wait(&a_full[kb], it & 1);
+                        const uint64_t ah = umma_desc_k_sw128(smem_u32(sA + (0 * nkb + kb) * TC_ABLK));
+                        const uint64_t al = umma_desc_k_sw128(smem_u32(sA + (1 * nkb + kb) * TC_ABLK));
+                        for (int hl = 0; hl < 2; ++hl, ++bcount) {
+                            const int s = bcount % TC_BST;
+                            const long long tw0 = rec ? clock64() : 0;
+                            mbar_wait(&b_full[s], (bcount / TC_BST) & 1);
+                            if (rec) bwait += clock64() - tw0;
+                            tcgen05_fence_after();
+                            if (elect_one_sync()) {
+                                const uint64_t bd = umma_desc_k_sw128(smem_u32(sB + s * TC_BBLK));
+                                if (hl == 0) {
 #pragma unroll
-                            for (int ks = 0; ks < TC_KB / 16; ++ks) {
-                                umma_bf16_ss(d, ah + 2 * ks, bh + 2 * ks, idesc, (kb | ks) != 0);
-                                umma_bf16_ss(d, ah + 2 * ks, bl + 2 * ks, idesc, 1);
-                                umma_bf16_ss(d, al + 2 * ks, bh + 2 * ks, idesc, 1);
+                                    for (int ks = 0; ks < TC_KB / 16; ++ks) {           // hi x hi, lo x hi
+                                        umma_bf16_ss(d, ah + 2 * ks, bd + 2 * ks, idesc, (kb | ks) != 0);
+                                        umma_bf16_ss(d, al + 2 * ks, bd + 2 * ks, idesc, 1);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int ks = 0; ks < TC_KB / 16; ++ks)             // hi x lo
+                                        umma_bf16_ss(d, ah + 2 * ks, bd + 2 * ks, idesc, 1);
+                                }
+                                umma_commit(&b_empty[s]);                        // slot may be refilled
+                                if (hl == 1) {
+                                    if (u == ub - 1) umma_commit(&a_empty[kb]);     // A block free for the next tile
+                                    if (kb == nkb - 1) umma_commit(&acc_full[ab]);
+                                }
                             }
-                            umma_commit(&b_empty[s]);                    // stage may be refilled
-                            if (u == TC_NU - 1) umma_commit(&a_empty[kb]);  // A block free for the next tile
-                            if (kb == nkb - 1) umma_commit(&acc_full[ab]);
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
+                    if (rec) { dbg[acount * 8 + 2] = bwait; dbg[acount * 8 + 3] = clock64(); }
                 }
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
+        // Thread = accumulator row (tile pixel p); its 21 outputs of halo row hrl are columns
+        // [px_t, px_t + 21) of that row's 36: a per-lane register shift (4 conditional stages of 8/4/2/1)
+        // instead of a round trip through shared memory -- the kernel is bound by shared-memory
+        // bandwidth (MMA operand reads + TMA writes), and the staging rows cost ~1.7K wavefronts per unit.
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;          // halo rows {2 half, 2 half + 1} of every unit
         const int p = quad * 32 + lane;            // tile pixel = TMEM lane = accumulator row
         const int py_t = p >> 4, px_t = p & 15;
-        float *row = sE + p * TC_EPITCH;
         // 1/(k*k*C): exact for power-of-two C (FlowNetC: 256) -> bit-identical to the reference's divide;
         // otherwise within 1 ulp.  (An IEEE divide here costs a slow-path call + reconvergence barrier
         // per output and serialises the epilogue: measured 13K cycles per unit.)
         const float inv_nelems = 1.0f / (float)C;
         const long plane = (long)H * W;
+        const bool s8 = px_t & 8, s4 = px_t & 4, s2 = px_t & 2, s1 = px_t & 1;
         uint32_t acount = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const TcTile T = tc_decode(t, nxt, nyt);
+        TcSeg sg;
+        for (int tn = blockIdx.x, w = w0; tc_next_seg(tn, w, full, w1, sg);) {
+            const int ua = sg.ua, ub = sg.ub;
+            const TcTile T = tc_decode(sg.t, nxt, nyt);
             const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
             const bool pix_ok = (yc < Hc) && (xc < Wc);
             float *obase = out + (long)T.n * (TC_DS * TC_DS) * plane + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
-            for (int u = 0; u < TC_NU; ++u, ++acount) {
+            for (int u = ua; u < ub; ++u, ++acount) {
                 const int ab = acount % TC_NACC;
+                const bool rec = dbg && blockIdx.x == 0 && acount < 64 && p == 0 && half == 0;
+                if (rec) dbg[acount * 8 + 4] = clock64();
                 mbar_wait(&acc_full[ab], (acount / TC_NACC) & 1);
+                if (rec) dbg[acount * 8 + 5] = clock64();
                 tcgen05_fence_after();
 #pragma unroll 1
-                for (int hrl = 0; hrl < TC_UR; ++hrl) {
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int hrl = 2 * half + hh;
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ab * TC_N + hrl * TC_HW;
                     float r[TC_HW];
                     tmem_ld16(taddr, r);
@@ -255,17 +321,23 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
                     tmem_ld4(taddr + 32, r + 32);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < TC_HW; ++j) row[j] = r[j];
+                    for (int j = 0; j < 28; ++j) r[j] = s8 ? r[j + 8] : r[j];
+#pragma unroll
+                    for (int j = 0; j < 24; ++j) r[j] = s4 ? r[j + 4] : r[j];
+#pragma unroll
+                    for (int j = 0; j < 22; ++j) r[j] = s2 ? r[j + 2] : r[j];
+#pragma unroll
+                    for (int j = 0; j < 21; ++j) r[j] = s1 ? r[j + 1] : r[j];
                     const int tj = u * TC_UR + hrl - py_t;          // = tj + DR, valid in [0, 20]
                     if (pix_ok && tj >= 0 && tj < TC_DS) {
                         float *o = obase + (long)(tj * TC_DS) * plane;
-                        const float *rp = row + px_t;
 #pragma unroll
-                        for (int ti = 0; ti < TC_DS; ++ti) __stcs(o + ti * plane, rp[ti] * inv_nelems);
+                        for (int ti = 0; ti < TC_DS; ++ti) __stcs(o + ti * plane, r[ti] * inv_nelems);
                     }
                 }
                 tcgen05_fence_before();
                 mbar_arrive(&acc_empty[ab]);
+                if (rec) dbg[acount * 8 + 6] = clock64();
             }
         }
     }
@@ -275,7 +347,7 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward on tensor cores.  WHICH == 1: gradInput1 (other = input2), WHICH == 2: gradInput2.
+// Backward on tensor cores: gradInput1 tiles (other = input2) and gradInput2 tiles (other = input1).
 //
 //   gI1[c, p] = 1/C sum_q G1[p, q] f2[c, q],   G1[p, q] = gO[(q - p), p]          (|q - p| <= 10)
 //   gI2[c, q] = 1/C sum_p G2[q, p] f1[c, p],   G2[q, p] = gO[(q - p), p]
@@ -305,27 +377,32 @@ constexpr int TB_ASTG = 2 * TB_AHL;                // 73728 B per A stage
 constexpr int TB_NAST = 2, TB_MAXBST = 6, TB_NACC = 2;
 constexpr int TB_SMEM_A = TB_NAST * TB_ASTG;       // 147456
 constexpr int TB_NBAR = 2 * TB_NAST + 2 * TB_MAXBST + 2 * TB_NACC;
-// B staging: the unit's 144 K indices in 3 groups of 48 (12 halo columns x 4 rows); one stage = one
-// group x one PAIR of 64-channel blocks, hi and lo = 4 boxes of 6 KB.  MMAs then cover N = 128 columns:
-// an N = 64 MMA re-reads the 4-KB A slice for 2 KB of B and the tensor pipe ran at ~65 cycles per
-// 32-cycle MMA (clock64 timeline); N = 256 stages do not fit next to the double-buffered A.
+// B staging: the unit's 144 K indices in 3 groups of 48 (12 halo columns x 4 rows); one half-stage = the
+// hi (or the lo) copy of one group x ALL channel blocks = up to 4 boxes of 6 KB, so every MMA covers N = C
+// columns: both operands come from shared memory (128 B/clk), an M128 x N x K16 MMA reads 4 KB of A and
+// N/32 KB of B, and the kernel is bound by that traffic -- N = 256 reads A half as often as N = 128 did.
 constexpr int TB_NG = 3, TB_GW = TC_HW / TB_NG, TB_GK = TC_UR * TB_GW;   // 3 groups, 12 columns, 48 K
 constexpr int TB_GBLK = TB_GK * 128;               // 6144 B: one 64-channel block of a group's rows
-constexpr int TB_BSTAGE = 4 * TB_GBLK;             // 24576 B: [hi|lo][2 channel blocks][48 rows x 128 B]
+constexpr int TB_BSTAGE = 4 * TB_GBLK;             // 24576 B: [<= 4 channel blocks][48 rows x 128 B]
 __host__ __device__ constexpr uint32_t tb_kindex(uint32_t hrl, uint32_t qx) {
     return (qx / TB_GW) * TB_GK + hrl * TB_GW + (qx % TB_GW);
 }
-constexpr int TB_THREADS = 704;                    // warp 0 TMA, 1 MMA, 2-17 builders, 18-21 epilogue
+constexpr int TB_MAXPROD = 3;                      // TMA producer warps (one batch in flight each, see the forward)
+constexpr int TB_THREADS = 704 + 32 * (TB_MAXPROD - 1);   // warp 0 TMA, 1 MMA, 2-17 builders, 18-21 epilogue, 22.. TMA
 __host__ __device__ constexpr int tb_smem_bytes(int bst) {
     return TB_SMEM_A + bst * TB_BSTAGE + TB_NBAR * 8 + 16 + 1024;
 }
 
 
-template <int WHICH>
+// Both gradients in ONE launch: global tiles [t_begin, t_end) of [0, 2 ntiles); tile g < ntiles is tile g of
+// gradInput1 (B = input2's halo, maps m2h / m2l), tile g >= ntiles is tile g - ntiles of gradInput2 (B = input1's
+// halo).  3584 tiles on 148 SMs waste 3 % in the last round, two launches of 1792 wasted 7 % each.
 __global__ void __launch_bounds__(TB_THREADS, 1)
-corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constant__ CUtensorMap mol,
-                   const float *__restrict__ gout, float *__restrict__ gin, int B, int C, int H, int W,
-                   int ntiles, int TB_NBST, int hint, long long *__restrict__ dbg) {
+corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap m2h, const __grid_constant__ CUtensorMap m2l,
+                   const __grid_constant__ CUtensorMap m1h, const __grid_constant__ CUtensorMap m1l,
+                   const float *__restrict__ gout, float *__restrict__ gin1, float *__restrict__ gin2, int B, int C,
+                   int H, int W, int ntiles, int t_begin, int t_end, int TB_NBST, int hint, int nprod,
+                   long long *__restrict__ dbg) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sA = smem;                          // [stage][hl][9 k-steps][2 chunks][16 groups][8 x 16 B]
@@ -343,7 +420,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
     const long plane = (long)H * W;
 
     if (tid == 0) {
-        prefetch_tensormap(&moh); prefetch_tensormap(&mol);
+        prefetch_tensormap(&m2h); prefetch_tensormap(&m2l);
+        prefetch_tensormap(&m1h); prefetch_tensormap(&m1l);
         for (int i = 0; i < TB_NAST; ++i) { mbar_init(&a_full[i], 16); mbar_init(&a_empty[i], 1); }   // one arrival per builder warp
         for (int i = 0; i < TB_MAXBST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < TB_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
@@ -358,33 +436,35 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ===================== TMA producer: the other input's halo chunks =====================
-        {
+    if (warp == 0 || warp >= 22) {
+        // ===================== TMA producers: the other input's halo chunks =====================
+        const int prod = warp == 0 ? 0 : warp - 21;
+        if (prod < nprod) {
             uint32_t bcount = 0;
             const uint64_t pol = l2_policy_evict_last();
             auto load = [&](void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3) {
                 if (hint) tma_load_4d_hint(dst, m, bar, c0, c1, c2, c3, pol);
                 else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
             };
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-                const TcTile T = tc_decode(t, nxt, nyt);
+            for (int g = t_begin + blockIdx.x; g < t_end; g += gridDim.x) {
+                const bool second = g >= ntiles;
+                const TcTile T = tc_decode(second ? g - ntiles : g, nxt, nyt);
                 const int img = T.n * 4 + T.py * 2 + T.px;
+                const CUtensorMap *moh = second ? &m1h : &m2h, *mol = second ? &m1l : &m2l;
+                // one half-stage = the hi (then the lo) copy of a K-group's 48 halo positions x all C channels:
+                // ncb boxes of 6 KB on one barrier
                 for (int u = 0; u < TC_NU; ++u)
                     for (int g = 0; g < TB_NG; ++g)
-                        for (int jp = 0; jp < ncb; jp += 2, ++bcount) {
+                        for (int hl = 0; hl < 2; ++hl, ++bcount) {
+                            if ((int)(bcount % (uint32_t)nprod) != prod) continue;
                             const int s = bcount % TB_NBST;
-                            const int nb = (ncb - jp) < 2 ? 1 : 2;     // channel blocks in this stage
                             mbar_wait(&b_empty[s], ((bcount / TB_NBST) & 1) ^ 1);
                             if (elect_one_sync()) {
-                                mbar_arrive_expect_tx(&b_full[s], (uint32_t)(2 * nb * TB_GBLK));
+                                mbar_arrive_expect_tx(&b_full[s], (uint32_t)(ncb * TB_GBLK));
                                 unsigned char *dst = sB + s * TB_BSTAGE;
-                                for (int j = 0; j < nb; ++j) {
-                                    load(dst + j * TB_GBLK, &moh, &b_full[s], (jp + j) * TC_KB, T.xc0 - TC_DR + g * TB_GW,
+                                for (int j = 0; j < ncb; ++j)
+                                    load(dst + j * TB_GBLK, hl ? mol : moh, &b_full[s], j * TC_KB, T.xc0 - TC_DR + g * TB_GW,
                                          T.yc0 - TC_DR + u * TC_UR, img);
-                                    load(dst + (2 + j) * TB_GBLK, &mol, &b_full[s], (jp + j) * TC_KB, T.xc0 - TC_DR + g * TB_GW,
-                                         T.yc0 - TC_DR + u * TC_UR, img);
-                                }
                             }
                             __syncwarp();
                         }
@@ -396,13 +476,13 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
         // commits.  (Issuing from `if (lane == 0)` made nvcc wrap every UTCHMMA in an
         // ELECT / BRA.U.ANY per-active-lane loop: ~70 cycles per MMA, measured.)
         {
-            const uint32_t idesc2 = umma_idesc_bf16_f32(128, 2 * TC_KB, 1, 1);   // N = 128, A and B MN-major
-            const uint32_t idesc1 = umma_idesc_bf16_f32(128, TC_KB, 1, 1);       // N = 64 (odd last channel block)
+            const uint32_t idesc = umma_idesc_bf16_f32(128, C, 1, 1);   // N = C (<= 256), A and B MN-major
             uint32_t bcount = 0, ucount = 0, tcount = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
+            for (int g = t_begin + blockIdx.x; g < t_end; g += gridDim.x, ++tcount) {
                 const int ab = tcount % TB_NACC;
                 mbar_wait(&acc_empty[ab], ((tcount / TB_NACC) & 1) ^ 1);
                 tcgen05_fence_after();
+                const uint32_t d = tmem_base + ab * 256;
                 for (int u = 0; u < TC_NU; ++u, ++ucount) {
                     const int as = ucount % TB_NAST;
                     const bool rec = dbg && blockIdx.x == 0 && ucount < 64 && lane == 0;
@@ -412,27 +492,26 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                     tcgen05_fence_after();
                     const uint32_t a_hi = smem_u32(sA + as * TB_ASTG), a_lo = a_hi + TB_AHL;
                     for (int g = 0; g < TB_NG; ++g)
-                        for (int jp = 0; jp < ncb; jp += 2, ++bcount) {
+                        for (int hl = 0; hl < 2; ++hl, ++bcount) {
                             const int s = bcount % TB_NBST;
                             mbar_wait(&b_full[s], (bcount / TB_NBST) & 1);
                             tcgen05_fence_after();
                             if (elect_one_sync()) {
-                                const uint32_t idesc = (ncb - jp) < 2 ? idesc1 : idesc2;
-                                const uint32_t bbase = smem_u32(sB + s * TB_BSTAGE);
-                                const uint64_t bh = umma_desc_mn_sw128(bbase, TB_GBLK);
-                                const uint64_t bl = umma_desc_mn_sw128(bbase + 2 * TB_GBLK, TB_GBLK);
-                                const uint32_t d = tmem_base + ab * 256 + jp * TC_KB;
+                                const uint64_t bd = umma_desc_mn_sw128(smem_u32(sB + s * TB_BSTAGE), TB_GBLK);
 #pragma unroll
                                 for (int ks = 0; ks < TB_GK / 16; ++ks) {
                                     const uint64_t ah = umma_desc_mn_sw128(a_hi + (g * TB_GK + ks * 16) * 128, TB_AMB);
-                                    const uint64_t al = umma_desc_mn_sw128(a_lo + (g * TB_GK + ks * 16) * 128, TB_AMB);
                                     const uint64_t kadv = (uint64_t)((ks * 16 * 128) >> 4);
-                                    umma_bf16_ss(d, ah, bh + kadv, idesc, (u | g | ks) != 0);
-                                    umma_bf16_ss(d, ah, bl + kadv, idesc, 1);
-                                    umma_bf16_ss(d, al, bh + kadv, idesc, 1);
+                                    if (hl == 0) {        // hi x hi, lo x hi
+                                        const uint64_t al = umma_desc_mn_sw128(a_lo + (g * TB_GK + ks * 16) * 128, TB_AMB);
+                                        umma_bf16_ss(d, ah, bd + kadv, idesc, (u | g | ks) != 0);
+                                        umma_bf16_ss(d, al, bd + kadv, idesc, 1);
+                                    } else {              // hi x lo
+                                        umma_bf16_ss(d, ah, bd + kadv, idesc, 1);
+                                    }
                                 }
                                 umma_commit(&b_empty[s]);
-                                if (g == TB_NG - 1 && jp + 2 >= ncb) umma_commit(&a_empty[as]);
+                                if (g == TB_NG - 1 && hl == 1) umma_commit(&a_empty[as]);
                             }
                             __syncwarp();
                         }
@@ -467,21 +546,22 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
             offs[jj] = two;
         }
         uint32_t ucount = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const TcTile T = tc_decode(t, nxt, nyt);
+        for (int g = t_begin + blockIdx.x; g < t_end; g += gridDim.x) {
+            const bool second = g >= ntiles;           // gradInput2 tile (warp-uniform)
+            const TcTile T = tc_decode(second ? g - ntiles : g, nxt, nyt);
             const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
             const bool pix_ok = (yc < Hc) && (xc < Wc);
             const int nbase = T.n * (TC_DS * TC_DS);
             // Per-tile address set-up (element offsets fit in 32 bits): for unit u the band row of halo
             // row hrl = 2hp+hh starts at off[hh] + u * dstep; consecutive displacements are `step` apart.
-            int off[2], dstep, step, tj0[2], ys0[2];
-            uint32_t colmask = 0;                                  // WHICH == 2: source columns inside the image
+            int off[2], dstep, step, ystep, tj0[2], ys0[2];
+            uint32_t colmask = 0;                                  // displacements to load (gradInput2: source columns inside the image)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const int hrl = 2 * hp + hh;
                 tj0[hh] = hrl - py_t;                              // tj + 10 at u = 0 (+4 per unit)
-                if (WHICH == 1) {
-                    ys0[hh] = 0;
+                if (!second) {
+                    ys0[hh] = pix_ok ? 0 : Hc;                     // gO at the output pixel itself
                     off[hh] = ((nbase + tj0[hh] * TC_DS + j0) * H + (2 * yc + T.py)) * W + (2 * xc + T.px);
                 } else {
                     ys0[hh] = T.yc0 - TC_DR + hrl;                 // source pixel row at u = 0 (+4 per unit)
@@ -494,10 +574,13 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
                             if ((unsigned)(xs0 + jj) < (unsigned)Wc) colmask |= 1u << jj;
                 }
             }
-            if (WHICH == 1) {
+            if (!second) {
                 step = iplane;                                     // next ti -> next plane
                 dstep = TC_UR * TC_DS * iplane;                    // next unit -> tj + 4
+                ystep = 0;
+                colmask = (1u << nj) - 1u;
             } else {
+                ystep = TC_UR;
                 step = 2 - iplane;                                 // j -> j+1: -1 plane, +2 in x
                 dstep = -TC_UR * TC_DS * iplane + 2 * TC_UR * W;   // next unit: tj + 4 -> -84 planes; source row + 4 -> +8 rows
                 colmask &= (1u << nj) - 1u;
@@ -509,13 +592,11 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int tjp = tj0[hh] + u * TC_UR;
-                    bool row_ok = (unsigned)tjp < (unsigned)TC_DS;
-                    if (WHICH == 1) row_ok = row_ok && pix_ok;
-                    else row_ok = row_ok && ((unsigned)(ys0[hh] + u * TC_UR) < (unsigned)Hc);
+                    const bool row_ok = ((unsigned)tjp < (unsigned)TC_DS) && ((unsigned)(ys0[hh] + u * ystep) < (unsigned)Hc);
                     const int base = off[hh] + u * dstep;      // only dereferenced under `ok`
 #pragma unroll
                     for (int jj = 0; jj < 11; ++jj) {
-                        const bool ok = row_ok && (WHICH == 1 ? (jj < nj) : ((colmask >> jj) & 1u));
+                        const bool ok = row_ok && ((colmask >> jj) & 1u);
                         v[hh][jj] = ok ? __ldg(gout + (base + jj * step)) : 0.f;
                     }
                 }
@@ -552,11 +633,12 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap moh, const __grid_constan
         const int py_t = p >> 4, px_t = p & 15;
         const float inv_nelems = 1.0f / (float)C;
         uint32_t tcount = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
-            const TcTile T = tc_decode(t, nxt, nyt);
+        for (int g = t_begin + blockIdx.x; g < t_end; g += gridDim.x, ++tcount) {
+            const bool second = g >= ntiles;
+            const TcTile T = tc_decode(second ? g - ntiles : g, nxt, nyt);
             const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
             const bool pix_ok = (yc < Hc) && (xc < Wc);
-            float *o = gin + (long)T.n * C * plane + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
+            float *o = (second ? gin2 : gin1) + (long)T.n * C * plane + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
             const int ab = tcount % TB_NACC;
             mbar_wait(&acc_full[ab], (tcount / TB_NACC) & 1);
             tcgen05_fence_after();
@@ -654,36 +736,45 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrPa
     cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "correlation_forward(tc): smem attribute (%s)", cudaGetErrorString(e));
     const int grid = ntiles < sms ? ntiles : sms;
-    corr_fwd_tc_kernel<<<grid, 192, smem, st>>>(m1h, m1l, m2h, m2l, out, p.B, p.C, p.H, p.W, ntiles, bst, hint);
+    // a producer may run at most one ring revolution ahead of the slot it refills: nprod <= slots
+    const int nprod = tc_env_int("FN2B200_TC_NP", TC_MAXPROD < bst ? TC_MAXPROD : bst, 1, TC_MAXPROD < bst ? TC_MAXPROD : bst);
+    long long *dbg = nullptr;          // FN2B200_TC_DBG = device pointer: per-unit clock64 timeline of CTA 0 (tools/tc_timeline.py)
+    if (const char *ev = getenv("FN2B200_TC_DBG")) dbg = reinterpret_cast<long long *>(strtoull(ev, nullptr, 0));
+    corr_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(m1h, m1l, m2h, m2l, out, p.B, p.C, p.H, p.W, ntiles, bst, hint, nprod,
+                                                        dbg);
     count_launch();
     return check_launch("correlation_forward(tc)");
 }
 
-template <int WHICH>
-static int launch_bwd_tc(const __nv_bfloat16 *oh, const __nv_bfloat16 *ol, const float *gout, float *gin,
-                         const CorrParams &p, cudaStream_t st) {
-    CUtensorMap moh, mol;
+static int launch_bwd_tc(const __nv_bfloat16 *h1, const __nv_bfloat16 *l1, const __nv_bfloat16 *h2, const __nv_bfloat16 *l2,
+                         const float *gout, float *gin1, float *gin2, const CorrParams &p, cudaStream_t st) {
+    CUtensorMap m1h, m1l, m2h, m2l;
     int rc;
-    if ((rc = make_class_map(&moh, oh, p, TB_GW, TC_UR))) return rc;     // one K group: 12 halo columns x 4 rows
-    if ((rc = make_class_map(&mol, ol, p, TB_GW, TC_UR))) return rc;
+    if ((rc = make_class_map(&m1h, h1, p, TB_GW, TC_UR))) return rc;     // one K group: 12 halo columns x 4 rows
+    if ((rc = make_class_map(&m1l, l1, p, TB_GW, TC_UR))) return rc;
+    if ((rc = make_class_map(&m2h, h2, p, TB_GW, TC_UR))) return rc;
+    if ((rc = make_class_map(&m2l, l2, p, TB_GW, TC_UR))) return rc;
     const int Hc = p.H / 2, Wc = p.W / 2;
     const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
     const int ntiles = p.B * 4 * nxt * nyt;
+    const int t_begin = gin1 ? 0 : ntiles, t_end = gin2 ? 2 * ntiles : ntiles;
+    if (t_end <= t_begin) return 0;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    auto kern = corr_bwd_tc_kernel<WHICH>;
     int bst = 2;
     while (bst < TB_MAXBST && tb_smem_bytes(bst + 1) <= TC_SMEM_MAX) ++bst;
     bst = tc_env_int("FN2B200_TC_BST", bst, 2, bst);
     const int hint = tc_env_int("FN2B200_TC_HINT", 1, 0, 1);
     const int smem = tb_smem_bytes(bst);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(corr_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "correlation_backward(tc): smem attribute (%s)", cudaGetErrorString(e));
-    const int grid = ntiles < sms ? ntiles : sms;
+    const int grid = (t_end - t_begin) < sms ? (t_end - t_begin) : sms;
     long long *dbg = nullptr;
-    if (const char *e = getenv("FN2B200_TC_DBG")) dbg = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
-    kern<<<grid, TB_THREADS, smem, st>>>(moh, mol, gout, gin, p.B, p.C, p.H, p.W, ntiles, bst, hint, dbg);
+    if (const char *ev = getenv("FN2B200_TC_DBG")) dbg = reinterpret_cast<long long *>(strtoull(ev, nullptr, 0));
+    const int nprod = tc_env_int("FN2B200_TC_NP", TB_MAXPROD < bst ? TB_MAXPROD : bst, 1, TB_MAXPROD < bst ? TB_MAXPROD : bst);
+    corr_bwd_tc_kernel<<<grid, TB_THREADS, smem, st>>>(m2h, m2l, m1h, m1l, gout, gin1, gin2, p.B, p.C, p.H, p.W, ntiles, t_begin,
+                                                       t_end, bst, hint, nprod, dbg);
     count_launch();
     return check_launch("correlation_backward(tc)");
 }
@@ -700,9 +791,7 @@ int corr_backward_tc(const float *in1, const float *in2, const float *gout, floa
     __nv_bfloat16 *w = static_cast<__nv_bfloat16 *>(workspace);
     int rc = 0;
     if (!have_split && (rc = corr_tc_split(in1, in2, w, p, st))) return rc;
-    if (gin1 && (rc = launch_bwd_tc<1>(w + 2 * per, w + 3 * per, gout, gin1, p, st))) return rc;
-    if (gin2 && (rc = launch_bwd_tc<2>(w, w + per, gout, gin2, p, st))) return rc;
-    return 0;
+    return launch_bwd_tc(w, w + per, w + 2 * per, w + 3 * per, gout, gin1, gin2, p, st);
 }
 
 }  // namespace fn2

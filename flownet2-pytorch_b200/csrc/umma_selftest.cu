@@ -181,31 +181,36 @@ int umma_selftest2(const void *A, const void *Bt, float *D, int a_sw32, cudaStre
 // ------------------------------------------------------------------------------------------------
 namespace fn2 {
 
-__global__ void __launch_bounds__(64, 1)
+__global__ void __launch_bounds__(256, 1)
 tma_feed_kernel(const __grid_constant__ CUtensorMap map, long long *__restrict__ out, int C, int Hc, int Wc,
-                int nimg, int bw, int bh, int stages, int per_stage, int iters) {
+                int nimg, int bw, int bh, int stages, int per_stage, int iters, int warps) {
+    // `warps` producer warps, each with a private `stages`-deep ring (own slots, own barriers)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *smem0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int box_bytes = bw * bh * 128;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)stages * per_stage * box_bytes);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, wid = tid >> 5;
+    uint64_t *bars0 = reinterpret_cast<uint64_t *>(smem0 + (size_t)warps * stages * per_stage * box_bytes);
     if (tid == 0) {
-        for (int i = 0; i < stages; ++i) mbar_init(&bars[i], 1);
+        prefetch_tensormap(&map);
+        for (int i = 0; i < warps * stages; ++i) mbar_init(&bars0[i], 1);
         fence_barrier_init();
     }
     __syncthreads();
-    if (tid >= 32) return;
+    if (wid >= warps) return;
+    unsigned char *smem = smem0 + (size_t)wid * stages * per_stage * box_bytes;
+    uint64_t *bars = bars0 + wid * stages;
     const int nkb = C / 64, nxt = (Wc + 15) / 16, nyt = (Hc + 7) / 8;
     const int ntiles = nimg * nxt * nyt;
     long long t0 = 0, bytes = 0;
     int issued = 0, waited = 0;
-    auto issue = [&](int n) {
+    auto issue = [&](int n0) {
         // n-th stage of this CTA: tile, unit, k-block as the correlation kernels walk them
+        const int n = n0 * warps + wid;
         const int per_tile = 7 * nkb;
         const int tile = (blockIdx.x + (n / per_tile) * gridDim.x) % ntiles;
         const int u = (n % per_tile) / nkb, kb = n % nkb;
         const int img = tile / (nxt * nyt), yc0 = ((tile / nxt) % nyt) * 8, xc0 = (tile % nxt) * 16;
-        const int s = n % stages;
+        const int s = n0 % stages;
         if (elect_one_sync()) {
             mbar_arrive_expect_tx(&bars[s], (uint32_t)(per_stage * box_bytes));
             for (int b = 0; b < per_stage; ++b)
@@ -222,22 +227,135 @@ tma_feed_kernel(const __grid_constant__ CUtensorMap map, long long *__restrict__
         if (issued < iters) { issue(issued); ++issued; }
     }
     const long long t1 = clock64();
-    if (tid == 0) { out[2 * blockIdx.x] = t1 - t0; out[2 * blockIdx.x + 1] = bytes; }
+    if ((tid & 31) == 0) {
+        atomicMax((unsigned long long *)&out[2 * blockIdx.x], (unsigned long long)(t1 - t0));
+        atomicAdd((unsigned long long *)&out[2 * blockIdx.x + 1], (unsigned long long)bytes);
+    }
+}
+
+// Cluster variant: CTA rank 0 of each cluster issues every box with .multicast::cluster to all `cs`
+// CTAs (same smem offset, same barrier offset in each); a slot is re-armed once every CTA of the
+// cluster has seen it complete (remote arrivals on rank 0's `empty` barriers).  out[] as above, bytes =
+// what landed in that CTA.  Answers: is the ~28 B/clk/SM unicast ceiling an SM-ingest or an L2-side limit?
+__device__ __forceinline__ void tma_load_4d_mc(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2,
+                                               int c3, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
+        "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    asm volatile(
+        "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(64, 1)
+tma_feed_mc_kernel(const __grid_constant__ CUtensorMap map, long long *__restrict__ out, int C, int Hc, int Wc,
+                   int nimg, int bw, int bh, int stages, int per_stage, int iters, int cs_signed) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int cs = cs_signed < 0 ? -cs_signed : cs_signed, cs_mode = cs_signed < 0;
+    const int box_bytes = bw * bh * 128;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)stages * per_stage * box_bytes);
+    uint64_t *empty = full + stages;
+    const int tid = threadIdx.x;
+    const uint32_t rank = cluster_ctarank();
+    if (tid == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)cs); }
+        fence_barrier_init();
+    }
+    cluster_sync_all();
+    if (tid < 32) {
+        const int nkb = C / 64, nxt = (Wc + 15) / 16, nyt = (Hc + 7) / 8;
+        const int ntiles = nimg * nxt * nyt;
+        const int cid = blockIdx.x / cs, ncl = gridDim.x / cs;
+        const uint16_t mask = (uint16_t)((1u << cs) - 1u);
+        long long bytes = 0;
+        auto arm = [&](int n) {
+            if (elect_one_sync()) mbar_arrive_expect_tx(&full[n % stages], (uint32_t)(per_stage * box_bytes));
+            __syncwarp();
+        };
+        const bool all_issue = cs_mode != 0;       // every rank issues the boxes b % cs == rank
+        auto issue = [&](int n) {
+            const int per_tile = 7 * nkb;
+            const int tile = (cid + (n / per_tile) * ncl) % ntiles;
+            const int u = (n % per_tile) / nkb, kb = n % nkb;
+            const int img = tile / (nxt * nyt), yc0 = ((tile / nxt) % nyt) * 8, xc0 = (tile % nxt) * 16;
+            const int s = n % stages;
+            if (elect_one_sync())
+                for (int b = 0; b < per_stage; ++b)
+                    if (!all_issue || (uint32_t)(b % cs) == rank)
+                    tma_load_4d_mc(smem + ((size_t)s * per_stage + b) * box_bytes, &map, &full[s], kb * 64,
+                                   xc0 - 10 + (b * bw) % 36, yc0 - 10 + u * 4, (img + b) % nimg, mask);
+            __syncwarp();
+        };
+        int n = 0;
+        for (; n < stages && n < iters; ++n) { arm(n); if (rank == 0 || all_issue) issue(n); }
+        const long long t0 = clock64();
+        for (int w = 0; w < iters; ++w) {
+            const int s = w % stages;
+            mbar_wait(&full[s], (w / stages) & 1);
+            bytes += (long long)per_stage * box_bytes;
+            if (elect_one_sync()) {
+                if (all_issue) for (int r = 0; r < cs; ++r) mbar_arrive_remote(&empty[s], (uint32_t)r);
+                else mbar_arrive_remote(&empty[s], 0);
+            }
+            __syncwarp();
+            if (n < iters) {
+                arm(n);
+                if (rank == 0 || all_issue) { mbar_wait(&empty[s], (w / stages) & 1); issue(n); }
+                ++n;
+            }
+        }
+        const long long t1 = clock64();
+        if (tid == 0) { out[2 * blockIdx.x] = t1 - t0; out[2 * blockIdx.x + 1] = bytes; }
+    }
+    cluster_sync_all();     // nobody leaves while a peer may still signal its barriers
 }
 
 int tma_feed_bench(const void *base, long long *out, int nimg, int C, int Hc, int Wc, int bw, int bh, int stages,
-                   int per_stage, int iters, int grid, cudaStream_t st) {
+                   int per_stage, int iters, int grid, int cluster, int warps, cudaStream_t st) {
     CUtensorMap m;
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wc, (uint64_t)Hc, (uint64_t)nimg};
     uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)Wc * C * 2, (uint64_t)Hc * Wc * C * 2};
     uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bh, 1u};
     int rc = make_tensor_map_bf16_sw128(&m, base, 4, dims, strides, box);
     if (rc) return rc;
-    const int smem = stages * per_stage * bw * bh * 128 + stages * 8 + 1024 + 64;
+    if (warps < 1 || warps > 8) return fail(FN2B200_EINVAL, "tma_feed_bench: producer warps %d", warps);
+    const int smem = warps * (stages * per_stage * bw * bh * 128 + 2 * stages * 8) + 1024 + 64;
     if (smem > 232448) return fail(FN2B200_EINVAL, "tma_feed_bench: %d bytes of shared memory requested", smem);
-    cudaError_t e = cudaFuncSetAttribute(tma_feed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail((int)e, "tma_feed_bench: smem attribute (%s)", cudaGetErrorString(e));
-    tma_feed_kernel<<<grid, 64, smem, st>>>(m, out, C, Hc, Wc, nimg, bw, bh, stages, per_stage, iters);
+    const int cmode = cluster;                 // negative: every rank issues its share of the boxes
+    if (cluster < -1) cluster = -cluster;
+    if (cluster <= 1) {
+        cudaError_t e = cudaFuncSetAttribute(tma_feed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail((int)e, "tma_feed_bench: smem attribute (%s)", cudaGetErrorString(e));
+        cudaMemsetAsync(out, 0, sizeof(long long) * 2 * grid, st);
+        tma_feed_kernel<<<grid, 256, smem, st>>>(m, out, C, Hc, Wc, nimg, bw, bh, stages, per_stage, iters, warps);
+    } else {
+        if (cluster > 8 || grid % cluster) return fail(FN2B200_EINVAL, "tma_feed_bench: cluster %d, grid %d", cluster, grid);
+        cudaError_t e = cudaFuncSetAttribute(tma_feed_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail((int)e, "tma_feed_bench: smem attribute (%s)", cudaGetErrorString(e));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, tma_feed_mc_kernel, m, out, C, Hc, Wc, nimg, bw, bh, stages, per_stage, iters, cmode);
+        if (e != cudaSuccess) return fail((int)e, "tma_feed_bench: cluster launch (%s)", cudaGetErrorString(e));
+    }
     count_launch();
     return check_launch("tma_feed_bench");
 }

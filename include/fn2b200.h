@@ -173,10 +173,13 @@ int fn2b200_debug_umma_gemm(const void *A_bf16, const void *B_bf16, float *D, in
 /*
  * TMA feed micro-benchmark (tools/tma_feed.py): persistent CTAs pull halo-style SW128 boxes
  * (64 channels x box_w x box_h) of a [nimg][Hc][Wc][C] bf16 tensor into a `stages`-deep ring with no
- * consumer; out[2*cta] = cycles, out[2*cta+1] = bytes.  Test / tuning hook only.
+ * consumer; out[2*cta] = cycles, out[2*cta+1] = bytes.  cluster > 1: thread-block clusters of that size, rank 0
+ * issues every box with TMA multicast to the whole cluster (cluster < -1: every rank issues its share).
+ * producer_warps (1..8, unicast only): that many warps each drive a private ring.  Test / tuning hook only.
  */
 int fn2b200_debug_tma_feed(const void *base_bf16, long long *out, int nimg, int C, int Hc, int Wc, int box_w,
-                           int box_h, int stages, int boxes_per_stage, int iters, int grid, void *stream);
+                           int box_h, int stages, int boxes_per_stage, int iters, int grid, int cluster,
+                           int producer_warps, void *stream);
 
 /* Number of kernel launches (ours) issued by this library in this process so far (statistics). */
 uint64_t fn2b200_launch_count(void);

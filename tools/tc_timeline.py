@@ -15,6 +15,21 @@ b = torch.randn(8, C, 112, 256, device=dev, generator=g)
 go = torch.randn(8, 441, 112, 256, device=dev, generator=g)
 _, ws = F2.correlation_forward(a, b, 20, 1, 20, 1, 2, return_workspace=True)
 F2.correlation_backward(a, b, go, 20, 1, 20, 1, 2, need2=False, workspace=ws)   # warm
+if len(sys.argv) > 2 and sys.argv[2] == "fwd":
+    dbg = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
+    os.environ["FN2B200_TC_DBG"] = str(dbg.data_ptr())
+    F2.correlation_forward(a, b, 20, 1, 20, 1, 2)
+    torch.cuda.synchronize()
+    del os.environ["FN2B200_TC_DBG"]
+    d = dbg.cpu().view(64, 8).tolist()
+    t0 = d[0][0]
+    print("C=%d forward, per unit (cycles rel. to first): MMA[start acc_ok end | acc.wait b.wait total]  EPI[start full_ok done | wait work]" % C)
+    for u in range(0, 44):
+        r = d[u]
+        print("%3d  M %7d %7d %7d | %5d %5d %5d   E %7d %7d %7d | %5d %5d" % (
+            u, r[0] - t0, r[1] - t0, r[3] - t0, r[1] - r[0], r[2], r[3] - r[0], r[4] - t0, r[5] - t0, r[6] - t0,
+            r[5] - r[4], r[6] - r[5]))
+    sys.exit(0)
 dbg = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
 os.environ["FN2B200_TC_DBG"] = str(dbg.data_ptr())
 F2.correlation_backward(a, b, go, 20, 1, 20, 1, 2, need2=False, workspace=ws)
