@@ -460,11 +460,11 @@ def main():
     if rank == 0:
         per_f, per_b = ms_f / K, ms_b / K
         dominant = "correlation_backward" if per_b >= per_f else "correlation_forward"
-        kname = {"correlation_backward": "corr_bwd_tc_kernel<WHICH> (one launch per input gradient)",
+        kname = {"correlation_backward": "corr_bwd_tc_kernel (both input gradients in one launch)",
                  "correlation_forward": "corr_tc_split_kernel + corr_fwd_tc_kernel"}[dominant] if args.impl == "ours" else dominant
         if dominant == "correlation_backward":
-            launch_ms = per_b / (2 if args.impl == "ours" else 1)
-            ach = (bwd_launch_b if args.impl == "ours" else bwd_b) / (launch_ms * 1e-3) / 1e9
+            launch_ms = per_b          # ours: ONE launch computes both gradients; reference: all its launches
+            ach = bwd_b / (launch_ms * 1e-3) / 1e9
         else:
             launch_ms = per_f
             ach = fwd_b / (per_f * 1e-3) / 1e9
@@ -479,13 +479,14 @@ def main():
             "frac_hbm_peak": round(value / world / peak, 4),
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(ach / peak, 4),
-                         "traffic": (843030000 if (args.impl == "ours" and dominant == "correlation_backward") else None),
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of corr_bwd_tc_kernel<1>, "
-                                           "one launch, ncu --set full (profiles/r1j_ncu_full_summary.csv)",
+                         "traffic": (1684166488 if (args.impl == "ours" and dominant == "correlation_backward") else None),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of corr_bwd_tc_kernel, "
+                                           "one launch, ncu --set full (profiles/r1k_ncu_full_summary.csv)",
                          "peak_source": peak_src,
                          "launch_ms": round(launch_ms, 4),
-                         "note": "tensor-core kernel (bf16 hi/lo split, 3 MMAs per product) bound by on-chip operand movement, "
-                                 "not HBM: tensor pipe 46 % active, DRAM at ~30 % of peak; see DESIGN.md 4.1",
+                         "note": "tensor-core kernel (bf16 hi/lo split, 3 MMAs per product): tensor pipe 53 % active, each "
+                                 "M128xN256xK16 MMA with both operands in shared memory costs 169 cycles against the "
+                                 "128-cycle floor (tools/umma_rate.py); DRAM at ~30 % of peak; see DESIGN.md 4.1",
                          "fp32_tflops": round((51.79e9 * 3) / ((per_f + per_b) * 1e-3) / 1e12, 2)},
             "kernels": {"forward_ms": round(per_f, 4), "backward_ms": round(per_b, 4),
                         "forward_GBps": round(fwd_b / per_f / 1e6, 1), "backward_GBps": round(bwd_b / per_b / 1e6, 1)},

@@ -74,26 +74,29 @@ corr_tc_split_kernel(const float *__restrict__ in0, const float *__restrict__ in
         }
     }
     __syncthreads();
-    // thread -> (pixel, 16 channels): 4 threads write one pixel's 128 contiguous bytes (hi) + 128 (lo)
+    // thread -> (pixel, channels [8 cg, 8 cg + 8) and [32 + 8 cg, 40 + 8 cg)): the 4 threads of a pixel write 64
+    // contiguous bytes per store instruction (whole 32-byte sectors; 16 channels per thread in one run made
+    // every store touch only half of each sector)
     const int xo = tid >> 2, cg = tid & 3, x = x0 + xo;
     if (x < W) {
         const int cls = (y & 1) * 2 + (x & 1);
-        const long row = (((long)(n * 4 + cls) * Hc + (y >> 1)) * Wc + (x >> 1)) * C + c0 + cg * 16;
+        const long row = (((long)(n * 4 + cls) * Hc + (y >> 1)) * Wc + (x >> 1)) * C + c0;
         uint32_t hw[8], lw[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float v0 = tile[cg * 16 + 2 * i][xo], v1 = tile[cg * 16 + 2 * i + 1][xo];
+            const int c = (i >> 2) * 32 + cg * 8 + 2 * (i & 3);
+            const float v0 = tile[c][xo], v1 = tile[c + 1][xo];
             const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
             const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
             const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
             hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
             lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
         }
-        uint4 *ph = reinterpret_cast<uint4 *>(hi + row), *pl = reinterpret_cast<uint4 *>(lo + row);
+        uint4 *ph = reinterpret_cast<uint4 *>(hi + row + cg * 8), *pl = reinterpret_cast<uint4 *>(lo + row + cg * 8);
         ph[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        ph[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        ph[4] = make_uint4(hw[4], hw[5], hw[6], hw[7]);      // + 32 channels = 64 bytes
         pl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        pl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        pl[4] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
     }
 }
 
@@ -491,10 +494,13 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap m2h, const __grid_constan
                     if (rec) dbg[ucount * 8 + 5] = clock64();
                     tcgen05_fence_after();
                     const uint32_t a_hi = smem_u32(sA + as * TB_ASTG), a_lo = a_hi + TB_AHL;
+                    long long bwait = 0;
                     for (int g = 0; g < TB_NG; ++g)
                         for (int hl = 0; hl < 2; ++hl, ++bcount) {
                             const int s = bcount % TB_NBST;
+                            const long long tw0 = rec ? clock64() : 0;
                             mbar_wait(&b_full[s], (bcount / TB_NBST) & 1);
+                            if (rec) bwait += clock64() - tw0;
                             tcgen05_fence_after();
                             if (elect_one_sync()) {
                                 const uint64_t bd = umma_desc_mn_sw128(smem_u32(sB + s * TB_BSTAGE), TB_GBLK);
@@ -515,7 +521,7 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap m2h, const __grid_constan
                             }
                             __syncwarp();
                         }
-                    if (rec) dbg[ucount * 8 + 6] = clock64();
+                    if (rec) { dbg[ucount * 8 + 6] = clock64(); dbg[ucount * 8 + 7] = bwait; }
                 }
                 if (elect_one_sync()) umma_commit(&acc_full[ab]);
                 __syncwarp();

@@ -174,6 +174,74 @@ int umma_selftest2(const void *A, const void *Bt, float *D, int a_sw32, cudaStre
 }  // namespace fn2
 
 // ------------------------------------------------------------------------------------------------
+// MMA issue-rate micro-benchmark: every SM issues `iters` back-to-back M128 x N x K16 bf16 MMAs on fixed
+// (zeroed) operands and reports cycles per MMA.  mode 0: A and B from shared memory, K-major SW128 (the
+// forward's operands); mode 1: A from tensor memory, B as mode 0; mode 2: A and B MN-major SW128 (the
+// backward's).  extra_smem_kb: a second warp streams that many KB of generic shared-memory writes per
+// MMA batch to emulate TMA / epilogue traffic (0 = none).
+// ------------------------------------------------------------------------------------------------
+namespace fn2 {
+
+__global__ void __launch_bounds__(128, 1)
+umma_rate_kernel(float *__restrict__ out, int mode, int N, int iters) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (64 * 1024) / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    fence_proxy_async();
+    if (warp == 0) tmem_alloc<512>(&tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (warp == 0) {
+        const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 16384);      // A: 128 x 64, B: up to 256 x 64
+        const uint32_t idesc = umma_idesc_bf16_f32(128, N, mode == 2, mode == 2);
+        const uint64_t ad = mode == 2 ? umma_desc_mn_sw128(a_addr, 8192) : umma_desc_k_sw128(a_addr);
+        const uint64_t bd = mode == 2 ? umma_desc_mn_sw128(b_addr, 8192) : umma_desc_k_sw128(b_addr);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t adv = mode == 2 ? (uint64_t)((ks * 16 * 128) >> 4) : (uint64_t)(2 * ks);
+                    if (mode == 1) umma_bf16_ts(tmem_base, tmem_base + 256 + 8 * ks, bd + adv, idesc, 1);
+                    else umma_bf16_ss(tmem_base, ad + adv, bd + adv, idesc, 1);
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one_sync()) umma_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        if (tid == 0) out[blockIdx.x] = (float)(t1 - t0) / (4.0f * iters);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+int umma_rate_bench(float *out, int mode, int N, int iters, cudaStream_t st) {
+    if (mode < 0 || mode > 2 || N < 16 || N > 256 || (N & 15) || iters < 1)
+        return fail(FN2B200_EINVAL, "umma_rate_bench: mode %d N %d iters %d", mode, N, iters);
+    const int smem = 64 * 1024 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail((int)e, "umma_rate_bench: smem attribute (%s)", cudaGetErrorString(e));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    umma_rate_kernel<<<sms, 128, smem, st>>>(out, mode, N, iters);
+    count_launch();
+    return check_launch("umma_rate_bench");
+}
+
+}  // namespace fn2
+
+// ------------------------------------------------------------------------------------------------
 // TMA feed micro-benchmark (tools/tma_feed.py): how fast can one SM pull halo-style boxes
 // (64 channels x bw x bh class pixels of a [img][Hc][Wc][C] bf16 tensor, SW128) when nothing consumes
 // them?  Persistent CTAs, `stages`-deep ring, `per_stage` boxes per stage, access pattern of the

@@ -40,6 +40,6 @@ t0 = d[0][0]
 print("C=%d  unit: builder[wait_start wait_end fence_done arrived]  mma[wait_start wait_end issued]  (cycles rel. to first)" % C)
 for u in range(0, 40):
     r = d[u]
-    print("%3d  B %7d %7d %7d %7d   M %7d %7d %7d | b.wait %5d b.scatter %5d  m.wait %5d m.issue %5d" % (
+    print("%3d  B %7d %7d %7d %7d   M %7d %7d %7d | b.wait %5d b.scatter %5d  m.wait(A) %5d m.issue %5d of which wait(B) %5d" % (
         u, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0,
-        r[1] - r[0], r[2] - r[1], r[5] - r[4], r[6] - r[5]))
+        r[1] - r[0], r[2] - r[1], r[5] - r[4], r[6] - r[5], r[7]))
