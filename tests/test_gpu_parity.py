@@ -325,6 +325,37 @@ needs_ref = pytest.mark.skipif(not oref.available(), reason="oracle/_ref referen
 
 
 @needs_ref
+def test_host_pipeline_matches_resident_results():
+    """flownet2_b200.hostpipe.HostPipeline: 5 steps with different host inputs through 2 buffer slots give, for
+    every step, exactly what the resident call gives (stream / event ordering of slot reuse)."""
+    f = _f2()
+    prm = (20, 1, 20, 1, 2)
+    shape = (2, 64, 16, 32)
+    D, oH, oW = f.functional.correlation_out_shape(shape[1], shape[2], shape[3], *prm)
+    oshape = (shape[0], D, oH, oW)
+    pipe = f.hostpipe.HostPipeline([shape, shape, oshape], [oshape, shape, shape], "cuda:0", depth=2)
+
+    def compute(din, dout):
+        _, ws = f.functional.correlation_forward(din[0], din[1], *prm, 1, out=dout[0], return_workspace=True)
+        f.functional.correlation_backward(din[0], din[1], din[2], *prm, 1, out1=dout[1], out2=dout[2], workspace=ws)
+
+    steps = []
+    for i in range(5):
+        hin = [_randn(shape, 100 + i).pin_memory(), _randn(shape, 200 + i).pin_memory(), _randn(oshape, 300 + i).pin_memory()]
+        hout = [torch.empty(oshape).pin_memory(), torch.empty(shape).pin_memory(), torch.empty(shape).pin_memory()]
+        pipe.submit(compute, hin, hout)
+        steps.append((hin, hout))
+    pipe.drain()
+    torch.cuda.synchronize()
+    for hin, hout in steps:
+        a, b, go = (t.cuda() for t in hin)
+        out = f.functional.correlation_forward(a, b, *prm, 1)
+        g1, g2 = f.functional.correlation_backward(a, b, go, *prm, 1)
+        assert torch.equal(hout[0], out.cpu()) and torch.equal(hout[1], g1.cpu()) and torch.equal(hout[2], g2.cpu())
+    with pytest.raises(RuntimeError):
+        pipe.submit(compute, [torch.empty(shape)] * 2 + [torch.empty(oshape)], steps[0][1])   # not pinned
+
+
 @pytest.mark.parametrize("shape", [(1, 256, 48, 64), (2, 20, 13, 36)])
 def test_correlation_vs_reference_kernels(shape):
     f = _f2()
