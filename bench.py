@@ -191,10 +191,24 @@ def time_rotating(make_call, nsets, reps=3):
     return out[len(out) // 2]
 
 
+def load_host_pipeline(impl):
+    """The package's HostPipeline; for the reference arm the module (stream plumbing only, imports nothing but torch)
+    is loaded by path so that libfn2b200.so stays out of that process."""
+    if impl == "ours":
+        from flownet2_b200.hostpipe import HostPipeline
+        return HostPipeline
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_fn2_hostpipe", os.path.join(ROOT, "flownet2-pytorch_b200", "hostpipe.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.HostPipeline
+
+
 def flownet2_pairs_per_sec(impl, dev, model_name="FlowNet2", batch=8, steps=5, warmup=2):
     """BASELINE configs[3]/[4]: the UNMODIFIED reference models.py (baseline/_ref) on top of our layers
     (B2 hooks) or of the reference's own kernels; random xavier weights, U(0,255) input
-    [batch,3,2,448,1024], no_grad; H2D copy of the pinned input and D2H of the flow inside the loop."""
+    [batch,3,2,448,1024], no_grad; H2D copy of the pinned input and D2H of the flow inside the loop
+    (hostpipe.HostPipeline: they overlap with the previous / next batch's kernels, for both arms)."""
     import torch
     from types import SimpleNamespace
     from oracle import ref as oref
@@ -213,24 +227,27 @@ def flownet2_pairs_per_sec(impl, dev, model_name="FlowNet2", batch=8, steps=5, w
     net = getattr(models, model_name)(SimpleNamespace(rgb_max=255.0, fp16=False)).to(dev).eval()
     host = (torch.rand(batch, 3, 2, 448, 1024) * 255.0).pin_memory()
     hout = torch.empty(batch, 2, 448, 1024).pin_memory()
-    x = torch.empty(host.shape, device=dev)
+    pipe = load_host_pipeline(impl)([host.shape], [hout.shape], dev, depth=2)
 
-    def step():
-        x.copy_(host, non_blocking=True)
+    def compute(din, dout):
         with torch.no_grad():
-            y = net(x)
-        hout.copy_(y, non_blocking=True)
+            dout[0].copy_(net(din[0]))
+
+    def step():          # H2D of the next batch and D2H of the previous flow overlap with the network
+        pipe.submit(compute, (host,), (hout,))
     for _ in range(warmup):
         step()
+    pipe.drain()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         step()
+    pipe.drain()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    del net
+    del net, pipe
     torch.cuda.empty_cache()
     return {"model": model_name, "batch_per_gpu": batch, "ms_per_batch": round(ms, 3),
             "pairs_per_sec_per_gpu": round(batch / ms * 1e3, 2), "finite": bool(torch.isfinite(hout).all())}
@@ -421,14 +438,7 @@ def main():
     # Public entry point for host-resident data: flownet2_b200.hostpipe.HostPipeline (three streams, two sets of
     # device buffers): every step copies all three inputs H2D and all three results D2H; the D2H of step i and
     # the H2D of step i+1 share the full-duplex link.  Both arms go through the same pipeline.
-    if args.impl == "ours":
-        from flownet2_b200.hostpipe import HostPipeline
-    else:      # stream plumbing only (imports nothing but torch): loaded by path so that libfn2b200.so stays out of this arm
-        import importlib.util
-        _spec = importlib.util.spec_from_file_location("_fn2_hostpipe", os.path.join(ROOT, "flownet2-pytorch_b200", "hostpipe.py"))
-        _mod = importlib.util.module_from_spec(_spec)
-        _spec.loader.exec_module(_mod)
-        HostPipeline = _mod.HostPipeline
+    HostPipeline = load_host_pipeline(args.impl)
     pipe = HostPipeline([f1.shape, f2.shape, gO.shape], [out.shape, g1.shape, g2.shape], dev, depth=2)
 
     def e2e_compute(din, dout):
@@ -507,9 +517,9 @@ def main():
             "frac_hbm_peak": round(value / world / peak, 4),
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(ach / peak, 4),
-                         "traffic": (1687369264 if (args.impl == "ours" and dominant == "correlation_backward") else None),
+                         "traffic": (1678070960 if (args.impl == "ours" and dominant == "correlation_backward") else None),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of corr_bwd_tc_kernel, "
-                                           "one launch, ncu --set full (profiles/r1l_ncu_full_summary.csv)",
+                                           "one launch, ncu --set full (profiles/r1m_ncu_full_summary.csv)",
                          "peak_source": peak_src,
                          "launch_ms": round(launch_ms, 4),
                          "note": "tensor-core kernel (bf16 hi/lo split, 3 MMAs per product): tensor pipe 53 % active, each "
