@@ -92,9 +92,36 @@ def test_correlation_tc_matches_fma_path(monkeypatch):
     assert 0 < e1 < 5e-5 and 0 < e2 < 5e-5, (e1, e2)
     only1, none2 = f.functional.correlation_backward(a, b, go, 20, 1, 20, 1, 2, need2=False)
     assert none2 is None and rel_err(only1.cpu().numpy(), g1_fma.cpu().numpy()) < 5e-5
+    # one launch computes both gradients (tiles [0, n) and [n, 2n)); each half on its own must give the same bits
+    none1, only2 = f.functional.correlation_backward(a, b, go, 20, 1, 20, 1, 2, need1=False)
+    assert none1 is None and torch.equal(only2, g2_tc) and torch.equal(only1, g1_tc)
     # badly scaled inputs: the hi/lo split must not lose the small operand
     out_tc = f.functional.correlation_forward(a * 1e-3, b * 3e4, 20, 1, 20, 1, 2)
     assert rel_err(out_tc.cpu().numpy(), (out_fma * 30.0).cpu().numpy()) < 5e-5
+
+
+def test_correlation_tc_partial_last_round_and_producer_counts(monkeypatch):
+    """160 tiles on 148 SMs: the forward deals the 12 tiles of the last, partial round out unit by unit, the
+    backward runs 320 tiles in one launch.  Checked against the oracle; the number of TMA producer warps
+    (FN2B200_TC_NP) must not change a single bit."""
+    f = _f2()
+    shape = (5, 64, 32, 128)                       # 5 x 4 classes x (16/8) x (64/16) = 160 tiles
+    prm = (20, 1, 20, 1, 2)
+    assert f._lib.LIB.fn2b200_correlation_path(shape[1], shape[2], shape[3], *prm) == 2
+    a, b = _randn(shape, 70), _randn(shape, 71)
+    out = f.functional.correlation_forward(a.cuda(), b.cuda(), *prm)
+    go = _randn(tuple(out.shape), 72)
+    g1, g2 = f.functional.correlation_backward(a.cuda(), b.cuda(), go.cuda(), *prm)
+    assert_close(out.cpu().numpy(), orc.correlation_forward(a.numpy(), b.numpy(), *prm), TOL, "corr fwd tail")
+    r1, r2 = orc.correlation_backward(a.numpy(), b.numpy(), go.numpy(), *prm)
+    assert_close(g1.cpu().numpy(), r1, TOL, "corr gI1 tail")
+    assert_close(g2.cpu().numpy(), r2, TOL, "corr gI2 tail")
+    for np_ in ("1", "2"):
+        monkeypatch.setenv("FN2B200_TC_NP", np_)
+        o2 = f.functional.correlation_forward(a.cuda(), b.cuda(), *prm)
+        h1, h2 = f.functional.correlation_backward(a.cuda(), b.cuda(), go.cuda(), *prm)
+        assert torch.equal(o2, out) and torch.equal(h1, g1) and torch.equal(h2, g2), np_
+    monkeypatch.delenv("FN2B200_TC_NP")
 
 
 def test_correlation_stride1_2_forward_only():
