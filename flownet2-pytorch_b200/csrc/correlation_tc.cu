@@ -1,4 +1,4 @@
-// correlation_tc.cu -- tensor-core (tcgen05 / TMEM) correlation FORWARD for FlowNetC's configuration
+// correlation_tc.cu -- tensor-core (tcgen05 / TMEM) correlation FORWARD and BACKWARD for FlowNetC's configuration
 // (kernel_size 1, stride1 1, stride2 2, displacement radius 10, pad == max_displacement).
 //
 // Formulation.  stride2 = 2 means output pixel (y,x) only meets f2 pixels of
@@ -11,16 +11,18 @@
 // fp32 accuracy on bf16 tensor cores: every operand is split x = hi + lo (two bf16, 16 significand
 // bits); S = hi*hi + hi*lo + lo*hi (3 MMAs, fp32 accumulate in TMEM), dropped lo*lo ~ 2^-18 relative.
 //
-// Pipeline (one persistent CTA per SM, warp-specialised, 192 threads):
+// Forward pipeline (one persistent CTA per SM, warp-specialised, 416 threads):
 //   prepass kernel : NCHW fp32 -> [n][class][yc][xc][c] bf16 hi / lo (channels contiguous = K-major)
-//   warp 0 (TMA)   : f1 tile  -> smem A [hi|lo][C/64][128 rows x 128 B]  (resident for the 7 units)
-//                    f2 units -> smem B ring [2 stages][hi|lo][144 rows x 128 B], 128-byte swizzle;
-//                    halo outside the image = TMA out-of-bounds zero fill = the layer's zero padding
-//   warp 1 (MMA)   : tcgen05.mma.kind::f16 M128 N144 K16, 3 products x 4 k-steps per 64-channel
-//                    stage, accumulators in TMEM (3 buffers x 144 columns), tcgen05.commit -> mbarriers
-//   warps 2-5      : tcgen05.ld the accumulator rows (lane = tile pixel), pick the 21 band entries of
-//                    each halo row through a per-thread shared-memory row (dynamic column offset),
-//                    scale by 1/C and store to out[n][(tj,ti)][y][x]
+//   warps 0, 10-12 : TMA producers (one batch in flight per warp, so the slots are dealt round-robin):
+//                    f1 tile  -> smem A [hi|lo][C/64][128 rows x 128 B]  (resident for the tile's units)
+//                    f2 units -> smem B ring of 4-5 slots, one slot = hi OR lo of a unit x 64 channels
+//                    [144 rows x 128 B] = one 18-KB box, 128-byte swizzle; halo outside the image = TMA
+//                    out-of-bounds zero fill = the layer's zero padding
+//   warp 1 (MMA)   : tcgen05.mma.kind::f16 M128 N144 K16; hi slot: hi*hi and lo*hi, lo slot: hi*lo, 4
+//                    k-steps each; accumulators in TMEM (3 buffers x 144 columns), tcgen05.commit -> mbarriers
+//   warps 2-9      : tcgen05.ld the accumulator rows (lane = tile pixel, two warps per lane quadrant), pick
+//                    the 21 band entries of each halo row with a per-lane register shift, scale by 1/C and
+//                    store to out[n][(tj,ti)][y][x]
 #include "umma.cuh"
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -356,13 +358,13 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
 //   gI2[c, q] = 1/C sum_p G2[q, p] f1[c, p],   G2[q, p] = gO[(q - p), p]
 // per parity class: D[128 tile px][C] += A[128][144] * B[144 halo px][C] over the 7 halo-row units,
 // accumulated in ONE TMEM buffer per tile (C <= 256 fp32 columns, double-buffered across tiles).
-//   A = the banded gradOutput matrix, built per unit by 4 "builder" warps straight from the fp32
-//       gradOutput planes (bf16 hi/lo split on the fly) into the K-major 32-byte-swizzle layout (the
-//       no-swizzle layout made the 2-byte band scatter 4-way bank conflicted: 70 % of wavefronts);
+//   A = the banded gradOutput matrix, built per unit by 16 "builder" warps straight from the fp32
+//       gradOutput planes (bf16 hi/lo split on the fly) into an MN-major SW128 layout [k][64 pixels]
+//       (K-major layouts made the 2-byte band scatter 4- to 6.5-way bank conflicted, ncu);
 //   B = the other input's halo chunk from the prepass copy ([pixel][channel] bf16 = MN-major operand),
-//       one 64-channel block per TMA stage;
-//   3 MMAs (hi*hi, hi*lo, lo*hi) per k-step, N = 128 per instruction (pairs of channel blocks).
-// Roles (704 threads): warp 0 TMA, warp 1 MMA, warps 2-17 builders, warps 18-21 epilogue.
+//       one slot = hi OR lo of a K-group (48 halo pixels) x all channel blocks;
+//   3 MMAs (hi*hi, lo*hi | hi*lo) per k-step, N = C <= 256 per instruction.
+// Roles (768 threads): warps 0, 22, 23 TMA, warp 1 MMA, warps 2-17 builders, warps 18-21 epilogue.
 // Builders: FOUR threads per tile pixel = (halo-row pair) x (displacement half); a single warp per
 // scheduler ran ~2000 dependent instructions per unit at IPC ~0.2 and made the builder -- not the
 // tensor pipe -- the bottleneck.  Loads stay coalesced (lanes = pixels, one displacement plane per
