@@ -399,9 +399,9 @@ __host__ __device__ constexpr int tb_smem_bytes(int bst) {
 }
 
 
-// Both gradients in ONE launch: global tiles [t_begin, t_end) of [0, 2 ntiles); tile g < ntiles is tile g of
-// gradInput1 (B = input2's halo, maps m2h / m2l), tile g >= ntiles is tile g - ntiles of gradInput2 (B = input1's
-// halo).  3584 tiles on 148 SMs waste 3 % in the last round, two launches of 1792 wasted 7 % each.
+// Both gradients in ONE launch: global tiles [t_begin, t_end) of [0, 2 ntiles).  One gradient only: tile g < ntiles
+// is tile g of gradInput1 (B = input2's halo, maps m2h / m2l), tile g >= ntiles is tile g - ntiles of gradInput2
+// (B = input1's halo); both: g = 2 tile + (0 = gradInput1, 1 = gradInput2).  3584 tiles on 148 SMs waste 3 % in the last round, two launches of 1792 wasted 7 % each.
 __global__ void __launch_bounds__(TB_THREADS, 1)
 corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap m2h, const __grid_constant__ CUtensorMap m2l,
                    const __grid_constant__ CUtensorMap m1h, const __grid_constant__ CUtensorMap m1l,
@@ -423,6 +423,9 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap m2h, const __grid_constan
     const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
     const int ncb = C / TC_KB;
     const long plane = (long)H * W;
+    // both gradients requested: even global tiles are gradInput1 tiles, odd ones the gradInput2 tile of the same
+    // location, so the two readers of a gradOutput region run side by side and the second one finds it in L2
+    const bool both = (t_begin == 0) && (t_end == 2 * ntiles);
 
     if (tid == 0) {
         prefetch_tensormap(&m2h); prefetch_tensormap(&m2l);
@@ -452,8 +455,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap m2h, const __grid_constan
                 else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
             };
             for (int g = t_begin + blockIdx.x; g < t_end; g += gridDim.x) {
-                const bool second = g >= ntiles;
-                const TcTile T = tc_decode(second ? g - ntiles : g, nxt, nyt);
+                const bool second = both ? (g & 1) : (g >= ntiles);
+                const TcTile T = tc_decode(both ? (g >> 1) : (second ? g - ntiles : g), nxt, nyt);
                 const int img = T.n * 4 + T.py * 2 + T.px;
                 const CUtensorMap *moh = second ? &m1h : &m2h, *mol = second ? &m1l : &m2l;
                 // one half-stage = the hi (then the lo) copy of a K-group's 48 halo positions x all C channels:
@@ -555,8 +558,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap m2h, const __grid_constan
         }
         uint32_t ucount = 0;
         for (int g = t_begin + blockIdx.x; g < t_end; g += gridDim.x) {
-            const bool second = g >= ntiles;           // gradInput2 tile (warp-uniform)
-            const TcTile T = tc_decode(second ? g - ntiles : g, nxt, nyt);
+            const bool second = both ? (g & 1) : (g >= ntiles);           // gradInput2 tile (warp-uniform)
+            const TcTile T = tc_decode(both ? (g >> 1) : (second ? g - ntiles : g), nxt, nyt);
             const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
             const bool pix_ok = (yc < Hc) && (xc < Wc);
             const int nbase = T.n * (TC_DS * TC_DS);
@@ -649,8 +652,8 @@ corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap m2h, const __grid_constan
         const float inv_nelems = 1.0f / (float)C;
         uint32_t tcount = 0;
         for (int g = t_begin + blockIdx.x; g < t_end; g += gridDim.x, ++tcount) {
-            const bool second = g >= ntiles;
-            const TcTile T = tc_decode(second ? g - ntiles : g, nxt, nyt);
+            const bool second = both ? (g & 1) : (g >= ntiles);
+            const TcTile T = tc_decode(both ? (g >> 1) : (second ? g - ntiles : g), nxt, nyt);
             const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
             const bool pix_ok = (yc < Hc) && (xc < Wc);
             float *o = (second ? gin2 : gin1) + (long)T.n * C * plane + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
