@@ -517,9 +517,9 @@ def main():
             "frac_hbm_peak": round(value / world / peak, 4),
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(ach / peak, 4),
-                         "traffic": (1678070960 if (args.impl == "ours" and dominant == "correlation_backward") else None),
+                         "traffic": (1381696768 if (args.impl == "ours" and dominant == "correlation_backward") else None),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of corr_bwd_tc_kernel, "
-                                           "one launch, ncu --set full (profiles/r1m_ncu_full_summary.csv)",
+                                           "one launch, ncu --set full (profiles/r1n_ncu_full_summary.csv)",
                          "peak_source": peak_src,
                          "launch_ms": round(launch_ms, 4),
                          "note": "tensor-core kernel (bf16 hi/lo split, 3 MMAs per product): tensor pipe 53 % active, each "
