@@ -114,6 +114,7 @@ int make_tensor_map_bf16_sw128(CUtensorMap *map, const void *base, int rank, con
 
 int umma_selftest(const void *A, const void *B, float *D, int K, cudaStream_t st);
 int umma_selftest2(const void *A, const void *Bt, float *D, int a_sw32, cudaStream_t st);
+int umma_selftest_ts(const void *A, const void *B, float *D, int K, cudaStream_t st);
 int umma_rate_bench(float *out, int mode, int N, int iters, cudaStream_t st);
 int tma_feed_bench(const void *base, long long *out, int nimg, int C, int Hc, int Wc, int bw, int bh, int stages,
                    int per_stage, int iters, int grid, int cluster, int warps, cudaStream_t st);
@@ -179,6 +180,7 @@ int fn2b200_debug_umma_gemm(const void *A_bf16, const void *B_bf16, float *D, in
         const int code = -K - 1000;
         return umma_rate_bench(D, code / 1000, code % 1000, 2000, (cudaStream_t)stream);
     }
+    if (K <= -500 && K > -1000) return umma_selftest_ts(A_bf16, B_bf16, D, -K - 500, (cudaStream_t)stream);
     if (K == -144 || K == -145) return umma_selftest2(A_bf16, B_bf16, D, K == -145, (cudaStream_t)stream);
     return umma_selftest(A_bf16, B_bf16, D, K, (cudaStream_t)stream);
 }

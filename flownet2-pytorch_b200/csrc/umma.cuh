@@ -137,6 +137,13 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float *r) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) r[i] = __uint_as_float(v[i]);
 }
+// registers -> TMEM: this thread's lane, 8 consecutive 32-bit columns starting at taddr's column
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *r) {
     uint32_t v[16];
     asm volatile(

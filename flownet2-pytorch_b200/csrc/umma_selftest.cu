@@ -85,6 +85,94 @@ int umma_selftest(const void *A, const void *B, float *D, int K, cudaStream_t st
 }  // namespace fn2
 
 // ------------------------------------------------------------------------------------------------
+// Variant TS (round-2 groundwork, tools/umma_ts_check.py; not yet used by a kernel): the same product as
+// variant 1 with A read from TENSOR MEMORY.  Thread = row m writes its K bf16 values with tcgen05.st, two per
+// 32-bit column (ASSUMED layout: column k/2 of lane m, even k in the low half); B comes through TMA as before.
+// ------------------------------------------------------------------------------------------------
+namespace fn2 {
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_ts_kernel(const __nv_bfloat16_raw *__restrict__ A, const __grid_constant__ CUtensorMap mapB,
+                        float *__restrict__ D, int K) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *sB = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [144 rows][128 B], SW128
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + ST_N * 128);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_tmem = tmem_base + 256;                      // columns [256, 256 + K/2)
+    {   // A row `tid` -> TMEM lane `tid` (warp w owns lanes [32w, 32w+32))
+        const unsigned short *arow = reinterpret_cast<const unsigned short *>(A) + (size_t)tid * K;
+        for (int c0 = 0; c0 < K / 2; c0 += 8) {
+            uint32_t r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                r[j] = (uint32_t)arow[2 * (c0 + j)] | ((uint32_t)arow[2 * (c0 + j) + 1] << 16);
+            tmem_st8(a_tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+        }
+        tmem_st_wait();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t idesc = umma_idesc_bf16_f32(ST_M, ST_N);
+    const int nkb = K / ST_KB;
+    for (int kb = 0; kb < nkb; ++kb) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bars[0], ST_N * 128);
+            tma_load_2d(sB, &mapB, &bars[0], kb * ST_KB, 0);
+            mbar_wait(&bars[0], kb & 1);
+            tcgen05_fence_after();
+            const uint64_t db = umma_desc_k_sw128(smem_u32(sB));
+#pragma unroll
+            for (int ks = 0; ks < ST_KB / 16; ++ks)
+                umma_bf16_ts(tmem_base, a_tmem + (kb * ST_KB + ks * 16) / 2, db + 2 * ks, idesc, (kb | ks) != 0);
+            umma_commit(&bars[1]);
+            mbar_wait(&bars[1], kb & 1);
+        }
+        __syncthreads();
+    }
+    tcgen05_fence_after();
+    for (int c0 = 0; c0 < ST_N; c0 += 16) {
+        float r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) D[tid * ST_N + c0 + j] = r[j];
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+int umma_selftest_ts(const void *A, const void *B, float *D, int K, cudaStream_t st) {
+    if (K <= 0 || K % ST_KB || K > 256) return fail(FN2B200_EINVAL, "umma_selftest_ts: K must be 64, 128, 192 or 256");
+    CUtensorMap mb;
+    uint64_t dimsB[2] = {(uint64_t)K, ST_N};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t boxB[2] = {ST_KB, ST_N};
+    int rc = make_tensor_map_bf16_sw128(&mb, B, 2, dimsB, str, boxB);
+    if (rc) return rc;
+    const int smem = ST_N * 128 + 1024 + 64;
+    cudaError_t e = cudaFuncSetAttribute(umma_selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail((int)e, "umma_selftest_ts: smem attribute (%s)", cudaGetErrorString(e));
+    umma_selftest_ts_kernel<<<1, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16_raw *>(A), mb, D, K);
+    count_launch();
+    return check_launch("umma_selftest_ts");
+}
+
+}  // namespace fn2
+
+// ------------------------------------------------------------------------------------------------
 // Variant 2 (the backward kernel's operand forms): D[128 x 64] = A[128 x K] * Bt[K x 64] with
 //   A : K-major, NO swizzle, written to shared memory by the threads themselves (core-matrix layout)
 //   Bt: MN-major (N contiguous), SW128, loaded by TMA from a row-major [K][64] bf16 matrix.

@@ -167,7 +167,9 @@ int fn2b200_correlation_path(int C, int H, int W, int pad_size, int kernel_size,
  * threads in the no-swizzle core-matrix layout, Bt ([K][N] row-major) loaded as an MN-major
  * SW128 operand; K == -145 is the same with A in the 32-byte-swizzle K-major layout.
  * Test hook only (tests/test_gpu_umma.py).
-  * K <= -1000: MMA issue-rate benchmark instead (A_bf16 / B_bf16 unused but non-null): K = -(1000 + 1000 * mode + N),
+  * -1000 < K <= -500: the K > 0 product with K' = -K - 500 (64...256) and A read from tensor memory (written there by
+ * the threads with tcgen05.st; groundwork for round 2, tools/umma_ts_check.py).
+ * K <= -1000: MMA issue-rate benchmark instead (A_bf16 / B_bf16 unused but non-null): K = -(1000 + 1000 * mode + N),
  * mode 0 = A, B from shared memory (K-major), 1 = A from tensor memory, 2 = A, B MN-major; D[sm] = cycles per
  * M128 x N x K16 MMA on that SM (D holds >= #SM floats).
  */
