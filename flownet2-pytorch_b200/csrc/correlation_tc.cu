@@ -754,8 +754,19 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrPa
     cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "correlation_forward(tc): smem attribute (%s)", cudaGetErrorString(e));
     const int grid = ntiles < sms ? ntiles : sms;
-    // a producer may run at most one ring revolution ahead of the slot it refills: nprod <= slots
-    const int nprod = tc_env_int("FN2B200_TC_NP", TC_MAXPROD < bst ? TC_MAXPROD : bst, 1, TC_MAXPROD < bst ? TC_MAXPROD : bst);
+    // Producer-count rules (mbarrier parity waits only tell adjacent phases apart, so a producer must never be two
+    // phases ahead of the consumer on a barrier it did not itself visit one phase earlier):
+    //  * B slots: a producer's previous B stage is nprod stages back, so it is at most nprod + slots stages ahead
+    //    of the MMA warp -> nprod <= slots keeps it within one ring revolution;
+    //  * A blocks: with C = 256 a segment has 4 A jobs + 8 B jobs per unit; for nprod in {1, 2, 4} the job count of
+    //    every segment is a multiple of nprod, so each producer owns fixed A blocks and revisits the same a_empty
+    //    barrier every segment (safe by induction).  For C < 256 the A blocks would rotate between producers that
+    //    can be several short segments ahead (deep ring, few stages per segment): one producer there.
+    int np_max = 1;
+    if (nkb == TC_MAXKB)
+        while (2 * np_max <= TC_MAXPROD && 2 * np_max <= bst) np_max *= 2;
+    int nprod = tc_env_int("FN2B200_TC_NP", np_max, 1, np_max);
+    while (nprod & (nprod - 1)) --nprod;          // power of two
     long long *dbg = nullptr;          // FN2B200_TC_DBG = device pointer: per-unit clock64 timeline of CTA 0 (tools/tc_timeline.py)
     if (const char *ev = getenv("FN2B200_TC_DBG")) dbg = reinterpret_cast<long long *>(strtoull(ev, nullptr, 0));
     corr_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(m1h, m1l, m2h, m2l, out, p.B, p.C, p.H, p.W, ntiles, bst, hint, nprod,
