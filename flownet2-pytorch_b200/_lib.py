@@ -56,10 +56,6 @@ def _load():
     lib.fn2b200_channelnorm_forward_16.restype = _c_int
     lib.fn2b200_channelnorm_backward_16.argtypes = [_c_ptr] * 4 + [_c_int] * 6 + [_c_ptr]
     lib.fn2b200_channelnorm_backward_16.restype = _c_int
-    lib.fn2b200_debug_umma_gemm.argtypes = [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr]
-    lib.fn2b200_debug_umma_gemm.restype = _c_int
-    lib.fn2b200_debug_tma_feed.argtypes = [_c_ptr, _c_ptr] + [_c_int] * 12 + [_c_ptr]
-    lib.fn2b200_debug_tma_feed.restype = _c_int
     for name in ("correlation_out_shape", "correlation_path", "correlation_forward",
                  "correlation_backward", "resample2d_forward", "resample2d_backward",
                  "channelnorm_forward", "channelnorm_backward"):
@@ -79,7 +75,6 @@ SYMBOLS = (
     "fn2b200_resample2d_forward", "fn2b200_resample2d_backward",
     "fn2b200_channelnorm_forward", "fn2b200_channelnorm_backward",
     "fn2b200_channelnorm_forward_16", "fn2b200_channelnorm_backward_16",
-    "fn2b200_debug_umma_gemm", "fn2b200_debug_tma_feed",
 )
 
 

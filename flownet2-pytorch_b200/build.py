@@ -1,4 +1,5 @@
-"""Build libfn2b200.so (sm_100a) in-tree with nvcc -- no torch dependency, seconds per file.
+"""Build libfn2b200.so (the product) and libfn2b200_test.so (hardware self-tests and micro-benchmarks, csrc_test/) for
+sm_100a in-tree with nvcc -- no torch dependency, seconds per file.
 
     python flownet2-pytorch_b200/build.py [--force] [--verbose]
 
@@ -14,7 +15,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+CSRC_TEST = os.path.join(HERE, "csrc_test")
 LIB = os.path.join(HERE, "libfn2b200.so")
+LIB_TEST = os.path.join(HERE, "libfn2b200_test.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 
 NVCC_FLAGS = [
@@ -30,12 +33,25 @@ def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _digest():
+def _test_sources():
+    return sorted(f for f in os.listdir(CSRC_TEST) if f.endswith(".cu"))
+
+
+def _digest(product_only=False):
+    """sha1 over the sources and flags; product_only = the digest of what libfn2b200.so is built from (bench.py keys the
+    committed ncu figures in profiles/ on it)."""
     h = hashlib.sha1()
     for f in sorted(os.listdir(CSRC)) + ["../../include/fn2b200.h"]:
         h.update(open(os.path.join(CSRC, f), "rb").read())
+    if not product_only:
+        for f in sorted(os.listdir(CSRC_TEST)):
+            h.update(open(os.path.join(CSRC_TEST, f), "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
+
+
+def product_digest():
+    return _digest(product_only=True)
 
 
 def nvcc_path():
@@ -47,15 +63,17 @@ def nvcc_path():
 
 def build(force=False, verbose=False):
     digest = _digest()
-    if not force and os.path.isfile(LIB) and os.path.isfile(STAMP) and open(STAMP).read().strip() == digest:
+    if (not force and os.path.isfile(LIB) and os.path.isfile(LIB_TEST) and os.path.isfile(STAMP)
+            and open(STAMP).read().strip() == digest):
         return LIB
     obj_dir = os.path.join(HERE, "build")
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = nvcc_path()
 
-    def compile_one(src):
+    def compile_one(job):
+        src_dir, src = job
         obj = os.path.join(obj_dir, src[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", os.path.join(src_dir, src), "-o", obj]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         open(os.path.join(obj_dir, src[:-3] + ".ptxas.log"), "w").write(r.stdout)
         if r.returncode != 0:
@@ -64,15 +82,24 @@ def build(force=False, verbose=False):
             print(r.stdout)
         return obj
 
+    jobs = [(CSRC, f) for f in _sources()] + [(CSRC_TEST, f) for f in _test_sources()]
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
-        objs = list(ex.map(compile_one, _sources()))
-    tmp = LIB + ".tmp%d" % os.getpid()
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + ["-cudart", "static"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("link failed:\n" + r.stdout[-4000:])
-    os.replace(tmp, LIB)
+        objs = list(ex.map(compile_one, jobs))
+    n = len(_sources())
+
+    def link(out, objects):
+        tmp = out + ".tmp%d" % os.getpid()
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objects + ["-cudart", "static"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout[-4000:])
+        os.replace(tmp, out)
+
+    link(LIB, objs[:n])
+    # the test library carries its own copy of the host plumbing (runtime.o) -- it never links the product kernels
+    link(LIB_TEST, objs[n:] + [os.path.join(obj_dir, "runtime.o")])
     open(STAMP, "w").write(digest)
+    open(os.path.join(obj_dir, "product_digest.txt"), "w").write(product_digest())
     return LIB
 
 

@@ -17,6 +17,8 @@ namespace fn2 {
 void set_error(const char *fmt, ...);
 int fail(int code, const char *fmt, ...);
 void count_launch(int n = 1);
+uint64_t launches_so_far();
+const char *last_error_text();
 int check_launch(const char *what);
 int bind_device_of(const void *ptr);  // make the device owning ptr current on this thread  // cudaGetLastError -> return code (+ message)
 

@@ -1,7 +1,7 @@
 // umma_selftest.cu -- hardware self-test of the tcgen05 / TMEM / TMA-swizzle plumbing in umma.cuh.
 // D[128 x N] (fp32) = A[128 x K] * B[N x K]^T with bf16 operands, K a multiple of 64, N = 144.
-// Exposed as fn2b200_debug_umma_gemm (tests/test_gpu_umma.py compares with a CPU product).
-#include "umma.cuh"
+// Exposed through libfn2b200_test.so (csrc_test/fn2b200_test.h; tests/test_gpu_umma.py compares with a CPU product).
+#include "../csrc/umma.cuh"
 #include <cuda_bf16.h>
 
 namespace fn2 {

@@ -20,8 +20,11 @@
  *                                     (+ channelnorm_kernel.cu:131-177: K9)
  *
  * Conventions
- *   - All data pointers are DEVICE pointers to fp32, on the device that is current when the call
- *     is made.  Tensors are contiguous NCHW unless a stride array is passed.
+ *   - All data pointers are DEVICE pointers to fp32.  The device need not be current: every call
+ *     binds the calling thread to the device that owns its first data pointer
+ *     (cudaPointerGetAttributes + cudaSetDevice), so autograd worker threads and nn.DataParallel
+ *     replica threads can call in without a context.  Tensors are contiguous NCHW unless a stride
+ *     array is passed.
  *   - `stream` is a cudaStream_t / CUstream handle (NULL = legacy default stream).  Calls are
  *     asynchronous with respect to the host, like the reference (it never synchronises).
  *   - Return value: 0 on success; a negative FN2B200_E* code for argument errors; a positive
@@ -153,38 +156,12 @@ int fn2b200_channelnorm_backward_16(const void *input1, const void *output, cons
 
 /*
  * Introspection for benchmarks/tests: which kernel family the correlation entry points would
- * dispatch to for these parameters.  0 = generic gather kernels, 1 = TMA-tiled FMA kernels,
- * 2 = forward on tensor cores (when a workspace is supplied) + TMA-tiled FMA backward.
+ * dispatch to for these parameters.  0 = generic gather kernels, 1 = TMA-tiled FP32-FMA kernels,
+ * 2 = tensor cores (tcgen05) for forward AND backward when a workspace is supplied through the *_ws
+ * entry points (FN2B200_CORR_FWD=fma / FN2B200_CORR_BWD=fma select family 1 for that direction).
  */
 int fn2b200_correlation_path(int C, int H, int W, int pad_size, int kernel_size,
                              int max_displacement, int stride1, int stride2);
-
-/*
- * Hardware self-test of the tcgen05 / TMEM / TMA-swizzle plumbing the tensor-core correlation path
- * is built on: D[128 x 144] (fp32, row-major) = A[128 x K] * B[144 x K]^T, A and B bf16 row-major
- * device buffers, K a multiple of 64.  K == -144 selects the second form (the backward kernel's
- * operand layouts): D[128 x 64] = A[128 x 144] * Bt[144 x 64], A written to shared memory by the
- * threads in the no-swizzle core-matrix layout, Bt ([K][N] row-major) loaded as an MN-major
- * SW128 operand; K == -145 is the same with A in the 32-byte-swizzle K-major layout.
- * Test hook only (tests/test_gpu_umma.py).
-  * -1000 < K <= -500: the K > 0 product with K' = -K - 500 (64...256) and A read from tensor memory (written there by
- * the threads with tcgen05.st; groundwork for round 2, tools/umma_ts_check.py).
- * K <= -1000: MMA issue-rate benchmark instead (A_bf16 / B_bf16 unused but non-null): K = -(1000 + 1000 * mode + N),
- * mode 0 = A, B from shared memory (K-major), 1 = A from tensor memory, 2 = A, B MN-major; D[sm] = cycles per
- * M128 x N x K16 MMA on that SM (D holds >= #SM floats).
- */
-int fn2b200_debug_umma_gemm(const void *A_bf16, const void *B_bf16, float *D, int K, void *stream);
-
-/*
- * TMA feed micro-benchmark (tools/tma_feed.py): persistent CTAs pull halo-style SW128 boxes
- * (64 channels x box_w x box_h) of a [nimg][Hc][Wc][C] bf16 tensor into a `stages`-deep ring with no
- * consumer; out[2*cta] = cycles, out[2*cta+1] = bytes.  cluster > 1: thread-block clusters of that size, rank 0
- * issues every box with TMA multicast to the whole cluster (cluster < -1: every rank issues its share).
- * producer_warps (1..8, unicast only): that many warps each drive a private ring.  Test / tuning hook only.
- */
-int fn2b200_debug_tma_feed(const void *base_bf16, long long *out, int nimg, int C, int Hc, int Wc, int box_w,
-                           int box_h, int stages, int boxes_per_stage, int iters, int grid, int cluster,
-                           int producer_warps, void *stream);
 
 /* Number of kernel launches (ours) issued by this library in this process so far (statistics). */
 uint64_t fn2b200_launch_count(void);

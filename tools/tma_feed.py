@@ -6,7 +6,10 @@ import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from flownet2_b200._lib import LIB, check
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import testlib
+LIB = testlib.load()
+check = lambda rc, what: testlib.check(LIB, rc, what)
 dev = torch.device("cuda:0")
 nimg, Hc, Wc, C = 32, 56, 128, 256
 x = torch.randn(nimg, Hc, Wc, C, device=dev).bfloat16()
@@ -18,7 +21,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "all"
 def run(bw, bh, per, stages, grid=148, cluster=1, iters=600, warps=1):
     out.zero_()
     for rep in range(2):
-        check(LIB.fn2b200_debug_tma_feed(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), nimg, C, Hc, Wc,
+        check(LIB.fn2b200_test_tma_feed(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), nimg, C, Hc, Wc,
                                          bw, bh, stages, per, iters, grid, cluster, warps, st), "tma_feed")
         torch.cuda.synchronize()
     o = out.view(148, 2)[:grid].double()

@@ -5,7 +5,10 @@ import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from flownet2_b200._lib import LIB, check
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import testlib
+LIB = testlib.load()
+check = lambda rc, what: testlib.check(LIB, rc, what)
 dev = torch.device("cuda:0")
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 for K in (64, 128, 256):
@@ -13,8 +16,8 @@ for K in (64, 128, 256):
     A = torch.randn(128, K, device=dev, generator=g).bfloat16()
     B = torch.randn(144, K, device=dev, generator=g).bfloat16()
     D = torch.zeros(128, 144, device=dev)
-    check(LIB.fn2b200_debug_umma_gemm(ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()), ctypes.c_void_p(D.data_ptr()),
-                                      -(500 + K), st), "umma_ts")
+    check(LIB.fn2b200_test_umma_gemm_ts(ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()), ctypes.c_void_p(D.data_ptr()),
+                                        K, st), "umma_ts")
     torch.cuda.synchronize()
     ref = A.float() @ B.float().t()
     print("K=%3d  max|D - A B^T| / max|ref| = %.3e" % (K, float((D - ref).abs().max() / ref.abs().max())), flush=True)
