@@ -19,6 +19,11 @@ cpu_baseline : the CPU oracle (oracle/oracle.c, a port -- the reference has no C
                slice of the same workload, all host cores.
 --impl reference: the reference's OWN CUDA kernels rebuilt for sm_100a (oracle/_ref) on the same
                workload on the same GPU; if they are not built, the CPU oracle port instead.
+flownet2     : image-pairs/s of the unmodified reference models (random weights, 448x1024, bs 8 per GPU) on our
+               drop-in layers and through flownet2_b200.fused (glue folded into our kernels); `agreement` = max|d|/max|ref|
+               of the output flow against the same network on the reference's own kernels, same seeded input,
+               deterministic cuDNN, TF32 off (the reference output is computed in a child process: --flow-ref).
+Host staging buffers are allocated after binding the rank to its GPU's NUMA node (flownet2_b200.numa).
 """
 import argparse
 import json
@@ -191,6 +196,37 @@ def time_rotating(make_call, nsets, reps=3):
     return out[len(out) // 2]
 
 
+def load_by_path(name, filename):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "flownet2-pytorch_b200", filename))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def numa_bind(local):
+    """Pin this rank (CPU affinity + preferred memory node) to its GPU's NUMA node before any pinned allocation."""
+    try:
+        return load_by_path("_fn2_numa", "numa.py").bind_to_device_node(local)
+    except Exception as e:
+        return {"node": None, "error": str(e)[:100]}
+
+
+def profiled_traffic():
+    """dram__bytes_read+write per launch of the correlation kernels from a COMMITTED ncu capture (profiles/ncu_traffic.json),
+    valid only for the library sources it was taken on: keyed by the product source digest.  None when stale / absent."""
+    try:
+        digest = load_by_path("_fn2_build", "build.py").product_digest()
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = table.get(digest)
+        if ent:
+            ent = dict(ent)
+            ent["digest"] = digest
+        return ent
+    except Exception:
+        return None
+
+
 def load_host_pipeline(impl):
     """The package's HostPipeline; for the reference arm the module (stream plumbing only, imports nothing but torch)
     is loaded by path so that libfn2b200.so stays out of that process."""
@@ -204,74 +240,151 @@ def load_host_pipeline(impl):
     return mod.HostPipeline
 
 
-def flownet2_pairs_per_sec(impl, dev, model_name="FlowNet2", batch=8, steps=5, warmup=2):
-    """BASELINE configs[3]/[4]: the UNMODIFIED reference models.py (baseline/_ref) on top of our layers
-    (B2 hooks) or of the reference's own kernels; random xavier weights, U(0,255) input
-    [batch,3,2,448,1024], no_grad; H2D copy of the pinned input and D2H of the flow inside the loop
-    (hostpipe.HostPipeline: they overlap with the previous / next batch's kernels, for both arms)."""
+FLOW_SEED = 0
+
+
+def _flow_check_input(batch):
+    import torch
+    g = torch.Generator().manual_seed(1234)
+    return torch.rand(batch, 3, 2, 448, 1024, generator=g) * 255.0
+
+
+def _build_model(impl, model_name, dev):
     import torch
     from types import SimpleNamespace
     from oracle import ref as oref
-    if not oref.python_tree_available():
-        return {"unavailable": "baseline/_ref/flownet2_pytorch not installed (oracle/build_ref.py)"}
     if impl == "ours":
         from flownet2_b200 import compat
         compat.install("B2")
     else:
-        if not oref.available():
-            return {"unavailable": "oracle/_ref reference extensions not built"}
         oref.install_reference_extensions()
     models = oref.import_reference_models(fresh=True)
-    torch.backends.cudnn.benchmark = True
-    torch.manual_seed(0)
-    net = getattr(models, model_name)(SimpleNamespace(rgb_max=255.0, fp16=False)).to(dev).eval()
+    torch.manual_seed(FLOW_SEED)
+    return getattr(models, model_name)(SimpleNamespace(rgb_max=255.0, fp16=False)).to(dev).eval()
+
+
+def _deterministic(on):
+    import torch
+    torch.backends.cudnn.deterministic = on
+    torch.backends.cudnn.benchmark = not on
+    torch.backends.cudnn.allow_tf32 = not on
+    torch.backends.cuda.matmul.allow_tf32 = not on
+
+
+def flow_ref_child(model_names, out_dir, batch=8):
+    """--flow-ref: the reference kernels' output flow for the seeded check input, one .npy per model (child process of
+    the ours arm, so that the reference extensions never share a process with libfn2b200.so)."""
+    import numpy as np
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    _deterministic(True)
+    x = _flow_check_input(batch).to(dev)
+    for name in model_names:
+        net = _build_model("reference", name, dev)
+        with torch.no_grad():
+            np.save(os.path.join(out_dir, name + ".npy"), net(x).float().cpu().numpy())
+        del net
+        torch.cuda.empty_cache()
+
+
+def flownet2_pairs_per_sec(impl, dev, model_name="FlowNet2", batch=8, steps=5, warmup=2, ref_dir=None):
+    """BASELINE configs[3]/[4]: the UNMODIFIED reference models.py (baseline/_ref) on top of our layers
+    (B2 hooks) or of the reference's own kernels; random xavier weights, U(0,255) input
+    [batch,3,2,448,1024], no_grad; H2D copy of the pinned input and D2H of the flow inside the loop
+    (hostpipe.HostPipeline: they overlap with the previous / next batch's kernels, for both arms).
+    ours arm: also the fused forwards (flownet2_b200.fused) and the output-flow agreement with the reference kernels."""
+    import numpy as np
+    import torch
+    from oracle import ref as oref
+    if not oref.python_tree_available():
+        return {"unavailable": "baseline/_ref/flownet2_pytorch not installed (oracle/build_ref.py)"}
+    if impl != "ours" and not oref.available():
+        return {"unavailable": "oracle/_ref reference extensions not built"}
+    net = _build_model(impl, model_name, dev)
+    res = {"model": model_name, "batch_per_gpu": batch}
+    if impl == "ours":
+        from flownet2_b200 import fused
+        if ref_dir and os.path.isfile(os.path.join(ref_dir, model_name + ".npy")):
+            _deterministic(True)
+            ref = np.load(os.path.join(ref_dir, model_name + ".npy"))
+            xc = _flow_check_input(batch).to(dev)
+            with torch.no_grad():
+                o_mod = net(xc).float().cpu().numpy()
+            o_fus = fused.fused_forward(net, xc).float().cpu().numpy()
+            den = float(np.abs(ref).max())
+            res["agreement"] = {"what": "max|d|/max|ref| of the output flow vs the same network on the reference's kernels, "
+                                        "448x1024 bs %d, seeded input, deterministic cuDNN, TF32 off" % batch,
+                                "drop_in_modules": float(np.abs(o_mod - ref).max() / den),
+                                "fused_forward": float(np.abs(o_fus - ref).max() / den), "max_abs_ref": den}
+            del xc
+        else:
+            res["agreement"] = None
+    _deterministic(False)
     host = (torch.rand(batch, 3, 2, 448, 1024) * 255.0).pin_memory()
     hout = torch.empty(batch, 2, 448, 1024).pin_memory()
     pipe = load_host_pipeline(impl)([host.shape], [hout.shape], dev, depth=2)
 
-    def compute(din, dout):
-        with torch.no_grad():
-            dout[0].copy_(net(din[0]))
+    def timed(forward):
+        def compute(din, dout):
+            with torch.no_grad():
+                dout[0].copy_(forward(din[0]))
 
-    def step():          # H2D of the next batch and D2H of the previous flow overlap with the network
-        pipe.submit(compute, (host,), (hout,))
-    for _ in range(warmup):
-        step()
-    pipe.drain()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    pipe.drain()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+        def step():          # H2D of the next batch and D2H of the previous flow overlap with the network
+            pipe.submit(compute, (host,), (hout,))
+        for _ in range(warmup):
+            step()
+        pipe.drain()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        pipe.drain()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+    ms = timed(net)
+    res.update({"ms_per_batch": round(ms, 3), "pairs_per_sec_per_gpu": round(batch / ms * 1e3, 2),
+                "finite": bool(torch.isfinite(hout).all())})
+    if impl == "ours":
+        ms_f = timed(lambda x: fused.fused_forward(net, x))
+        res["fused"] = {"ms_per_batch": round(ms_f, 3), "pairs_per_sec_per_gpu": round(batch / ms_f * 1e3, 2),
+                        "finite": bool(torch.isfinite(hout).all()),
+                        "what": "flownet2_b200.fused: correlation + LeakyReLU written into the 473-channel concat; upsample + warp + "
+                                "diff + channel-norm + concat groups as one kernel each"}
     del net, pipe
     torch.cuda.empty_cache()
-    return {"model": model_name, "batch_per_gpu": batch, "ms_per_batch": round(ms, 3),
-            "pairs_per_sec_per_gpu": round(batch / ms * 1e3, 2), "finite": bool(torch.isfinite(hout).all())}
+    return res
 
 
-def cpu_baseline_sample():
-    """CPU oracle port on ONE sample of the workload (1/8 step), all host cores."""
+def cpu_baseline_sample(runs=3):
+    """CPU oracle port on ONE sample of the workload (1/8 step), all host cores: median of `runs` warmed runs."""
     import numpy as np
     from oracle import cpu as orc
     rng = np.random.RandomState(0)
     shp = (1, CFG["C"], CFG["H"], CFG["W"])
     a, b = rng.randn(*shp).astype(np.float32), rng.randn(*shp).astype(np.float32)
     prm = (CFG["pad"], CFG["k"], CFG["md"], CFG["s1"], CFG["s2"])
-    orc.correlation_forward(a[:, :8, :8, :16], b[:, :8, :8, :16], *prm)   # build + warm
-    t0 = time.time()
-    out = orc.correlation_forward(a, b, *prm)
+    out = orc.correlation_forward(a, b, *prm)                      # build + warm (threads, pages)
     go = rng.randn(*out.shape).astype(np.float32)
-    t1 = time.time()
     orc.correlation_backward(a, b, go, *prm)
-    t2 = time.time()
+    tf, tb = [], []
+    for _ in range(runs):
+        t0 = time.time()
+        orc.correlation_forward(a, b, *prm)
+        t1 = time.time()
+        orc.correlation_backward(a, b, go, *prm)
+        t2 = time.time()
+        tf.append(t1 - t0)
+        tb.append(t2 - t1)
+    tf.sort()
+    tb.sort()
     fwd, bwd, _ = alg_bytes(1)
-    secs = (t1 - t0) + (t2 - t1)
+    secs = tf[len(tf) // 2] + tb[len(tb) // 2]
     return {"value": round((fwd + bwd) / secs / 1e9, 4), "unit": "GB/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "1 of 8 samples of the cfg2 step (fwd %.2fs + bwd %.2fs), OpenMP on all cores" % (t1 - t0, t2 - t1)}
+            "sample": "1 of 8 samples of the cfg2 step, median of %d warmed runs (fwd %.2fs + bwd %.2fs), OpenMP on all cores"
+                      % (runs, tf[len(tf) // 2], tb[len(tb) // 2])}
 
 
 def build_impl(impl, dev):
@@ -337,6 +450,35 @@ def extras_ours(dev):
     rec("channelnorm_bwd_c3", lambda i: (lambda: F2.channelnorm_backward(imgs[i], o1[i], o1[(i + 1) % NS], out=o3[i])), hw * 8)
     rec("channelnorm_fwd_c2", lambda i: (lambda: F2.channelnorm_forward(flows[i], out=o1[i])), hw * 3)
     rec("channelnorm_bwd_c2", lambda i: (lambda: F2.channelnorm_backward(flows[i], o1[i], o1[(i + 1) % NS], out=o2[i])), hw * 6)
+    # hot L2 (the same buffer set every launch; working sets of 117-191 MB vs 126 MB of L2: partly resident)
+    rec("resample2d_fwd_hotL2", lambda i: (lambda: F2.resample2d_forward(imgs[0], flows[0], out=o3[0])), hw * 8)
+    rec("resample2d_bwd_hotL2", lambda i: (lambda: F2.resample2d_backward(imgs[0], flows[0], gos[0], out1=o3[0], out2=o2[0])), hw * 13)
+    rec("channelnorm_fwd_c3_hotL2", lambda i: (lambda: F2.channelnorm_forward(imgs[0], out=o1[0])), hw * 4)
+    rec("channelnorm_bwd_c3_hotL2", lambda i: (lambda: F2.channelnorm_backward(imgs[0], o1[0], o1[1], out=o3[0])), hw * 8)
+    # sigma = 64 px flows: more than half of the taps clamp to the border
+    for fl in flows:
+        fl.mul_(16.0)
+    rec("resample2d_fwd_sigma64", lambda i: (lambda: F2.resample2d_forward(imgs[i], flows[i], out=o3[i])), hw * 8)
+    rec("resample2d_bwd_sigma64", lambda i: (lambda: F2.resample2d_backward(imgs[i], flows[i], gos[i], out1=o3[i], out2=o2[i])), hw * 13)
+    # upsample + warp + diff + channel-norm + concat as one kernel vs the chain of modules (models.py:130-138)
+    xs = [torch.rand(B, 6, H, W, device=dev, generator=g) - 0.5 for _ in range(4)]
+    lrs = [torch.randn(B, 2, H // 4, W // 4, device=dev, generator=g) * 0.2 for _ in range(4)]
+    cats = [torch.empty(B, 12, H, W, device=dev) for _ in range(4)]
+    up = torch.nn.Upsample(scale_factor=4, mode="bilinear")
+    rs_m, cn_m = flownet2_b200.Resample2d(), flownet2_b200.ChannelNorm()
+
+    def chain(i):
+        def run():
+            with torch.no_grad():
+                fl = up(lrs[i] * 20.0)
+                warped = rs_m(xs[i][:, 3:], fl)
+                torch.cat((xs[i], warped, fl / 20.0, cn_m(xs[i][:, :3] - warped)), dim=1, out=cats[i])
+        return run
+    alg_fused = hw * (6 + 12) + B * 2 * (H // 4) * (W // 4) * 4
+    rec("warp_concat_fused", lambda i: (lambda: F2.warp_concat_forward(xs[i], lrs[i], upsample="bilinear", flow_mul=20.0,
+                                                                        flow_div=20.0, out=cats[i])), alg_fused, 4)
+    rec("warp_concat_chain_of_modules", chain, alg_fused, 4)
+    del xs, lrs, cats
     del imgs, flows, gos, o3, o2, o1
     # correlation at the shape FlowNet2 really produces at 448x1024
     a = [torch.randn(8, 256, 56, 128, device=dev, generator=g) for _ in range(2)]
@@ -348,6 +490,28 @@ def extras_ours(dev):
     rec("correlation_fwd_56x128", lambda i: (lambda: F2.correlation_forward(a[i], b[i], 20, 1, 20, 1, 2, out=o[i])), 218595328, 2)
     rec("correlation_bwd_56x128", lambda i: (lambda: F2.correlation_backward(a[i], b[i], gO[i], 20, 1, 20, 1, 2, out1=g1[i], out2=g2[i])),
         336035840, 2)
+    # fused epilogue: LeakyReLU(0.1)(corr) written into channels 32.. of the 473-channel concat buffer
+    cat = [torch.empty(8, 473, 56, 128, device=dev) for _ in range(2)]
+    rec("correlation_fwd_cat_leaky_56x128", lambda i: (lambda: F2.correlation_forward_cat(a[i], b[i], cat[i], 32, 0.1, 20, 1, 20, 1, 2)),
+        218595328, 2)
+
+    def corr_chain(i):
+        def run():
+            torch.cat((cat[i][:, :32], torch.nn.functional.leaky_relu(F2.correlation_forward(a[i], b[i], 20, 1, 20, 1, 2, out=o[i]), 0.1, inplace=True)), 1)
+        return run
+    rec("correlation_fwd_then_leaky_then_cat_56x128", corr_chain, 218595328, 2)
+    del a, b, o, gO, g1, g2, cat
+    # a C < 256 shape (single TMA producer in the forward, 2 k-blocks): [8,128,112,256]
+    a = [torch.randn(8, 128, 112, 256, device=dev, generator=g) for _ in range(2)]
+    b = [torch.randn(8, 128, 112, 256, device=dev, generator=g) for _ in range(2)]
+    o = [torch.empty(8, 441, 112, 256, device=dev) for _ in range(2)]
+    g1 = [torch.empty_like(a[0]) for _ in range(2)]
+    g2 = [torch.empty_like(a[0]) for _ in range(2)]
+    nb_f = 4 * (2 * 8 * 128 * 112 * 256 + 8 * 441 * 112 * 256)
+    nb_b = 4 * (8 * 441 * 112 * 256 + 4 * 8 * 128 * 112 * 256)
+    rec("correlation_fwd_c128_112x256", lambda i: (lambda: F2.correlation_forward(a[i], b[i], 20, 1, 20, 1, 2, out=o[i])), nb_f, 2)
+    rec("correlation_bwd_c128_112x256", lambda i: (lambda: F2.correlation_backward(a[i], b[i], o[i], 20, 1, 20, 1, 2, out1=g1[i], out2=g2[i])),
+        nb_b, 2)
     return res
 
 
@@ -358,8 +522,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--flow-ref", nargs="+", metavar=("OUT_DIR", "MODEL"), help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.flow_ref:                      # child of the ours arm: reference-kernel output flows for the agreement check
+        flow_ref_child(args.flow_ref[1:], args.flow_ref[0])
+        return
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -370,6 +538,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_info = numa_bind(local)           # before any pinned allocation: staging buffers on the GPU's own NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -408,17 +577,32 @@ def main():
         if dist:
             dist.barrier()
 
-    def step():
-        fwd(f1, f2, out)
-        bwd(f1, f2, gO, g1, g2)
+    if args.impl == "ours":
+        # the call a user makes: the nn.Module (autograd Function) forward, then backward of both input gradients;
+        # the Function keeps the forward's bf16 hi/lo workspace for its backward
+        import flownet2_b200
+        corr = flownet2_b200.Correlation(CFG["pad"], CFG["k"], CFG["md"], CFG["s1"], CFG["s2"], 1)
+        f1.requires_grad_(True)
+        f2.requires_grad_(True)
+
+        def step():
+            o = corr(f1, f2)
+            torch.autograd.grad(o, (f1, f2), gO)
+        step_how = "flownet2_b200.Correlation module forward + autograd backward (torch.autograd.grad), both input gradients"
+    else:
+        def step():
+            fwd(f1, f2, out)
+            bwd(f1, f2, gO, g1, g2)
+        step_how = "correlation_cuda.forward + correlation_cuda.backward of the reference extension"
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     K, Wm = args.steps, args.warmup
+    steps_cap = None
     if args.impl == "reference":
-        K = min(K, 5)            # the reference backward takes ~0.5 s per step
-        Wm = 3
+        steps_cap = 5            # the reference backward takes ~0.4 s per step: keep the arm within minutes
+        K = min(K, steps_cap)
     l0 = launches()
     step()
     launches_timed = (launches() - l0) * K      # kernels launched per step x timed steps
@@ -426,6 +610,7 @@ def main():
     clocks = sampler.window(t0, t1) if rank == 0 else None
 
     # dominant-kernel timing (alone, same stream): forward kernel, backward kernels
+    f1, f2 = f1.detach(), f2.detach()
     ms_f, _, _ = time_loop(lambda: fwd(f1, f2, out), K, 2, sync)
     ms_b, _, _ = time_loop(lambda: bwd(f1, f2, gO, g1, g2), K, 2, sync)
 
@@ -476,9 +661,25 @@ def main():
     if not args.no_extras:
         del pipe, hf1, hf2, hgO, hout, hg1, hg2, f1, f2, out, gO, g1, g2
         torch.cuda.empty_cache()
-        for mname in (["FlowNet2C", "FlowNet2"] if world == 1 else ["FlowNet2"]):
+        mnames = ["FlowNet2C", "FlowNet2"] if world == 1 else ["FlowNet2"]
+        ref_dir = None
+        if args.impl == "ours" and rank == 0:
+            # reference-kernel output flows for the agreement check, from a child process (rank 0 only)
+            import tempfile
+            ref_dir = tempfile.mkdtemp(prefix="fn2_flowref_")
             try:
-                r = flownet2_pairs_per_sec(args.impl, dev, mname, batch=8, steps=4 if args.impl == "reference" else 8)
+                env = dict(os.environ, LOCAL_RANK=str(local))
+                for k in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+                    env.pop(k, None)
+                subprocess.run([sys.executable, os.path.abspath(__file__), "--flow-ref", ref_dir] + mnames, env=env, timeout=900,
+                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=False)
+            except Exception:
+                pass
+        if dist:
+            barrier()
+        for mname in mnames:
+            try:
+                r = flownet2_pairs_per_sec(args.impl, dev, mname, batch=8, steps=4 if args.impl == "reference" else 8, ref_dir=ref_dir)
             except Exception as e:
                 r = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
             if "ms_per_batch" in r:
@@ -506,6 +707,26 @@ def main():
         else:
             launch_ms = per_f
             ach = fwd_b / (per_f * 1e-3) / 1e9
+        # DRAM traffic per launch: from the committed ncu capture IF it was taken on exactly these library sources
+        # (profiles/ncu_traffic.json keyed by the source digest); never attached to the reference arm; null when stale.
+        prof = profiled_traffic() if args.impl == "ours" else None
+        traffic = traffic_fwd = None
+        if prof:
+            traffic = prof.get("corr_bwd_tc_kernel") if dominant == "correlation_backward" else (
+                (prof.get("corr_fwd_tc_kernel") or 0) + (prof.get("corr_tc_split_kernel") or 0) or None)
+            if prof.get("corr_fwd_tc_kernel") and prof.get("corr_tc_split_kernel"):
+                traffic_fwd = prof["corr_fwd_tc_kernel"] + prof["corr_tc_split_kernel"]
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": traffic,
+                    "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, %s (sources %s)"
+                                       % (prof.get("source", "profiles/"), prof["digest"][:12])) if prof else
+                                      "no committed ncu capture matches these library sources (profiles/ncu_traffic.json)",
+                    "traffic_forward_incl_split_pass": traffic_fwd,
+                    "algorithmic_bytes": bwd_b if dominant == "correlation_backward" else fwd_b,
+                    "peak_source": peak_src, "launch_ms": round(launch_ms, 4),
+                    "fp32_tflops": round((51.79e9 * 3) / ((per_f + per_b) * 1e-3) / 1e12, 2)}
+        if prof and prof.get("note"):
+            roofline["note"] = prof["note"]
         line = {
             "metric": "correlation_fwd_bwd_algorithmic_GBps", "value": round(value, 2), "unit": "GB/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 4),
@@ -513,19 +734,10 @@ def main():
             "config": {"workload": "Correlation(pad=20,k=1,md=20,s1=1,s2=2) fwd+bwd on fp32 [8,256,112,256] per GPU "
                                    "(BASELINE configs[1])", "per_gpu_batch": B, "global_batch": B * world,
                        "l2": "inputs+outputs 1.75 GB per step >> 126 MB L2 (no flush needed)",
-                       "parallelism": "replicas x%d (weak, no data-path collective)" % world, "impl": name},
+                       "parallelism": "replicas x%d (weak, no data-path collective)" % world, "impl": name,
+                       "step": step_how},
             "frac_hbm_peak": round(value / world / peak, 4),
-            "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(ach / peak, 4),
-                         "traffic": (1381696768 if (args.impl == "ours" and dominant == "correlation_backward") else None),
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of corr_bwd_tc_kernel, "
-                                           "one launch, ncu --set full (profiles/r1n_ncu_full_summary.csv)",
-                         "peak_source": peak_src,
-                         "launch_ms": round(launch_ms, 4),
-                         "note": "tensor-core kernel (bf16 hi/lo split, 3 MMAs per product): tensor pipe 53 % active, each "
-                                 "M128xN256xK16 MMA with both operands in shared memory costs 169 cycles against the "
-                                 "128-cycle floor (tools/umma_rate.py); DRAM at ~30 % of peak; see DESIGN.md 4.1",
-                         "fp32_tflops": round((51.79e9 * 3) / ((per_f + per_b) * 1e-3) / 1e12, 2)},
+            "roofline": roofline,
             "kernels": {"forward_ms": round(per_f, 4), "backward_ms": round(per_b, 4),
                         "forward_GBps": round(fwd_b / per_f / 1e6, 1), "backward_GBps": round(bwd_b / per_b / 1e6, 1)},
             "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -533,12 +745,14 @@ def main():
                     "how": "flownet2_b200.hostpipe.HostPipeline: pinned host buffers, H2D / kernels / D2H of consecutive "
                            "steps on three streams, 2 device buffer sets", "max_abs_diff_vs_resident": e2e_check},
             "gpu_launches": int(launches_timed),
+            "numa": numa_info,
             "clocks": clocks,
             "flownet2": flow,
         }
         if args.impl == "reference":
             line["impl"] = "reference"
             line["config"]["impl"] = "reference CUDA kernels rebuilt for sm_100a (oracle/_ref)"
+            line["steps_requested"], line["steps_cap"] = args.steps, steps_cap
         if world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline_sample()

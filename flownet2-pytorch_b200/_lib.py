@@ -44,12 +44,25 @@ def _load():
     lib.fn2b200_correlation_forward_workspace.restype = ctypes.c_size_t
     lib.fn2b200_correlation_forward_ws.argtypes = [_c_ptr] * 3 + [_c_int] * 10 + [_c_ptr, ctypes.c_size_t, _c_ptr]
     lib.fn2b200_correlation_forward_ws.restype = _c_int
+    lib.fn2b200_correlation_forward_cat.argtypes = ([_c_ptr] * 3 + [_c_int, _c_int, ctypes.c_float] + [_c_int] * 10
+                                                    + [_c_ptr, ctypes.c_size_t, _c_ptr])
+    lib.fn2b200_correlation_forward_cat.restype = _c_int
     lib.fn2b200_correlation_backward_workspace.argtypes = [_c_int] * 9
     lib.fn2b200_correlation_backward_workspace.restype = ctypes.c_size_t
     lib.fn2b200_correlation_backward_ws.argtypes = ([_c_ptr] * 5 + [_c_int] * 10 + [_c_ptr, ctypes.c_size_t, _c_int, _c_ptr])
     lib.fn2b200_correlation_backward_ws.restype = _c_int
     lib.fn2b200_resample2d_forward.argtypes = [_c_ptr, lp, _c_ptr, _c_ptr] + [_c_int] * 8 + [_c_ptr]
+    lib.fn2b200_resample2d_forward_up.argtypes = [_c_ptr, lp, _c_ptr, _c_int, _c_int, _c_int, ctypes.c_float, _c_ptr] + [_c_int] * 4 + [_c_ptr]
+    lib.fn2b200_resample2d_forward_up.restype = _c_int
+    lib.fn2b200_warp_concat_forward.argtypes = ([_c_ptr, lp, _c_int, _c_ptr, _c_int, _c_int, _c_int, ctypes.c_float, _c_ptr]
+                                                + [_c_int] * 5 + [ctypes.c_float] + [_c_int] * 5 + [_c_ptr])
+    lib.fn2b200_warp_concat_forward.restype = _c_int
     lib.fn2b200_resample2d_backward.argtypes = [_c_ptr, lp, _c_ptr, _c_ptr, _c_ptr, _c_ptr] + [_c_int] * 9 + [_c_ptr]
+    lib.fn2b200_resample2d_backward_workspace.argtypes = [lp] + [_c_int] * 6
+    lib.fn2b200_resample2d_backward_workspace.restype = ctypes.c_size_t
+    lib.fn2b200_resample2d_backward_ws.argtypes = ([_c_ptr, lp, _c_ptr, _c_ptr, _c_ptr, _c_ptr] + [_c_int] * 9
+                                                   + [_c_ptr, ctypes.c_size_t, _c_ptr])
+    lib.fn2b200_resample2d_backward_ws.restype = _c_int
     lib.fn2b200_channelnorm_forward.argtypes = [_c_ptr, _c_ptr] + [_c_int] * 5 + [_c_ptr]
     lib.fn2b200_channelnorm_backward.argtypes = [_c_ptr] * 4 + [_c_int] * 5 + [_c_ptr]
     lib.fn2b200_channelnorm_forward_16.argtypes = [_c_ptr, _c_ptr] + [_c_int] * 6 + [_c_ptr]
@@ -70,9 +83,11 @@ SYMBOLS = (
     "fn2b200_version", "fn2b200_last_error", "fn2b200_launch_count",
     "fn2b200_correlation_out_shape", "fn2b200_correlation_path",
     "fn2b200_correlation_forward", "fn2b200_correlation_backward",
-    "fn2b200_correlation_forward_workspace", "fn2b200_correlation_forward_ws",
+    "fn2b200_correlation_forward_workspace", "fn2b200_correlation_forward_ws", "fn2b200_correlation_forward_cat",
     "fn2b200_correlation_backward_workspace", "fn2b200_correlation_backward_ws",
     "fn2b200_resample2d_forward", "fn2b200_resample2d_backward",
+    "fn2b200_resample2d_forward_up", "fn2b200_warp_concat_forward",
+    "fn2b200_resample2d_backward_workspace", "fn2b200_resample2d_backward_ws",
     "fn2b200_channelnorm_forward", "fn2b200_channelnorm_backward",
     "fn2b200_channelnorm_forward_16", "fn2b200_channelnorm_backward_16",
 )

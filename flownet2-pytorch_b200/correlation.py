@@ -24,7 +24,10 @@ class CorrelationFunction(Function):
         ctx.stride1 = stride1
         ctx.stride2 = stride2
         ctx.corr_multiply = corr_multiply
-        keep = torch.is_grad_enabled() and (input1.requires_grad or input2.requires_grad)
+        # grad mode is always OFF inside Function.forward (autograd disables it), so is_grad_enabled() cannot be the
+        # test; needs_input_grad says whether a backward can follow (under no_grad the ctx -- and the workspace with
+        # it -- is dropped as soon as forward returns, so keeping it there costs nothing).
+        keep = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         out, ws = F2.correlation_forward(input1, input2, pad_size, kernel_size, max_displacement, stride1, stride2,
                                          corr_multiply, return_workspace=True)
         # tensor-core path: keep the bf16 hi/lo copies of the inputs for backward (the reference keeps

@@ -30,6 +30,8 @@ static int fill_corr_params(CorrParams &p, int B, int C, int H, int W, int pad, 
                     "max_displacement/kernel_size", p.oH, p.oW);
     if ((int64_t)B * C * H * W >= (1LL << 31) || (int64_t)B * p.D * p.oH * p.oW >= (1LL << 31))
         return fail(FN2B200_EINVAL, "correlation: tensor exceeds 2^31 elements");
+    p.out_bstride = (long)p.D * p.oH * p.oW;
+    p.leaky = 1.f;
     return 0;
 }
 
@@ -38,6 +40,22 @@ static int fill_corr_params(CorrParams &p, int B, int C, int H, int W, int pad, 
 static bool tc_enabled() {
     const char *e = getenv("FN2B200_CORR_FWD");
     return !(e && (e[0] == 'f' || e[0] == 'F'));
+}
+// FN2B200_RESAMPLE selects the Resample2d kernel family: "tile" (default; 2-D tiles, L1-cached gathers) or "row"
+// (round 1: one CTA = 256 pixels of a row; kept as the comparison point).
+enum { RS_TILE = 0, RS_ROW = 2 };
+static int rs_family() {
+    const char *e = getenv("FN2B200_RESAMPLE");
+    if (e && (e[0] == 'r' || e[0] == 'R' || e[0] == 'g' || e[0] == 'G')) return RS_ROW;
+    return RS_TILE;
+}
+// FN2B200_RS_BWD selects how the tile backward scatters the image gradient: "vec" (default: one 16-byte reduction per
+// tap into a pixel-interleaved scratch, then a transpose; needs C <= 3 and the workspace) or "planar" (one scalar
+// reduction per tap and channel straight into the gradient).
+static int rs_scatter() {
+    const char *e = getenv("FN2B200_RS_BWD");
+    if (e && (e[0] == 'p' || e[0] == 'P')) return 1;
+    return 2;
 }
 static bool tc_bwd_enabled() {
     const char *e = getenv("FN2B200_CORR_BWD");
@@ -112,6 +130,31 @@ int fn2b200_correlation_forward_ws(const float *in1, const float *in2, float *ou
         return corr_forward_tc(in1, in2, out, p, workspace, workspace_bytes, (cudaStream_t)stream);
     }
     return fn2b200_correlation_forward(in1, in2, out, B, C, H, W, pad, k, md, s1, s2, corr_type_multiply, stream);
+}
+
+int fn2b200_correlation_forward_cat(const float *in1, const float *in2, float *cat, int cat_channels, int ch_offset,
+                                    float leaky_slope, int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
+                                    int corr_type_multiply, void *workspace, size_t workspace_bytes, void *stream) {
+    (void)corr_type_multiply;
+    CorrParams p;
+    int rc = fill_corr_params(p, B, C, H, W, pad, k, md, s1, s2);
+    if (rc) return rc;
+    if (ch_offset < 0 || cat_channels < ch_offset + p.D)
+        return fail(FN2B200_EINVAL, "correlation_forward_cat: channels [%d, %d) do not fit a %d-channel buffer", ch_offset,
+                    ch_offset + p.D, cat_channels);
+    if ((int64_t)B * cat_channels * p.oH * p.oW >= (1LL << 31))
+        return fail(FN2B200_EINVAL, "correlation_forward_cat: tensor exceeds 2^31 elements");
+    if (B == 0) return 0;
+    if (!in1 || !in2 || !cat) return fail(FN2B200_ENULL, "correlation_forward_cat: null pointer");
+    p.out_bstride = (long)cat_channels * p.oH * p.oW;
+    p.leaky = leaky_slope;
+    float *out = cat + (long)ch_offset * p.oH * p.oW;
+    if ((rc = bind_device_of(in1))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (workspace && tc_enabled() && corr_tc_supported(p) && workspace_bytes >= corr_tc_workspace_bytes(p))
+        return corr_forward_tc(in1, in2, out, p, workspace, workspace_bytes, st);
+    if (corr_tiled_supported(p)) return corr_forward_tiled(in1, in2, out, p, st);
+    return corr_forward_generic(in1, in2, out, p, st);
 }
 
 int fn2b200_correlation_backward(const float *in1, const float *in2, const float *gout,
@@ -189,28 +232,113 @@ int fn2b200_resample2d_forward(const float *img, const int64_t *istride, const f
     if (B == 0) return 0;
     if (!img || !flow || !out) return fail(FN2B200_ENULL, "resample2d_forward: null pointer");
     if ((rc = bind_device_of(flow))) return rc;
-    return resample2d_forward(img, istride, flow, out, B, C, iH, iW, H, W, bilinear,
-                              (cudaStream_t)stream);
+    const int fam = rs_family();
+    FlowSrc fs = {flow, H, W, 0, 1.f};
+    WarpOut o = {out, C, -1, 0, 0, -1, -1, -1, 1.f};
+    if (fam == RS_ROW)
+        return resample2d_forward(img, istride, flow, out, B, C, iH, iW, H, W, bilinear, (cudaStream_t)stream);
+    return resample2d_forward_tile(img, istride, nullptr, nullptr, fs, o, B, C, H, W, bilinear, (cudaStream_t)stream);
 }
+
+static int check_flow_src(const char *who, const float *flow, int fh, int fw, int mode, int H, int W) {
+    if (!flow) return fail(FN2B200_ENULL, "%s: null flow pointer", who);
+    if (mode < 0 || mode > 2) return fail(FN2B200_EINVAL, "%s: upsample_mode %d (0 none, 1 bilinear x4, 2 nearest x4)", who, mode);
+    if (mode == 0 ? (fh != H || fw != W) : (fh * 4 != H || fw * 4 != W))
+        return fail(FN2B200_EINVAL, "%s: flow %d x %d does not match the %d x %d output for upsample_mode %d", who, fh, fw, H, W, mode);
+    return 0;
+}
+
+int fn2b200_resample2d_forward_up(const float *img, const int64_t *istride, const float *flow, int fh, int fw,
+                                  int upsample_mode, float flow_mul, float *out, int B, int C, int H, int W,
+                                  void *stream) {
+    int rc = check_resample("resample2d_forward_up", istride, B, C, H, W, H, W, 1);
+    if (rc) return rc;
+    if ((rc = check_flow_src("resample2d_forward_up", flow, fh, fw, upsample_mode, H, W))) return rc;
+    if (B == 0) return 0;
+    if (!img || !out) return fail(FN2B200_ENULL, "resample2d_forward_up: null pointer");
+    if ((rc = bind_device_of(flow))) return rc;
+    FlowSrc fs = {flow, fh, fw, upsample_mode, upsample_mode ? flow_mul : 1.f};
+    WarpOut o = {out, C, -1, 0, 0, -1, -1, -1, 1.f};
+    return resample2d_forward_tile(img, istride, nullptr, nullptr, fs, o, B, C, H, W, 1, (cudaStream_t)stream);
+}
+
+int fn2b200_warp_concat_forward(const float *x, const int64_t *xstride, int C, const float *flow, int fh, int fw,
+                                int upsample_mode, float flow_mul, float *cat, int cat_channels, int ch_x, int n_x,
+                                int ch_warped, int ch_flow, float flow_div, int ch_flow_norm, int ch_diff_norm, int B,
+                                int H, int W, void *stream) {
+    if (B < 0 || C < 1 || H <= 0 || W <= 0 || cat_channels < 1)
+        return fail(FN2B200_EINVAL, "warp_concat_forward: bad shape B=%d C=%d H=%d W=%d cat_channels=%d", B, C, H, W, cat_channels);
+    if (!xstride) return fail(FN2B200_ENULL, "warp_concat_forward: null stride array");
+    int rc = check_flow_src("warp_concat_forward", flow, fh, fw, upsample_mode, H, W);
+    if (rc) return rc;
+    struct { int ch, n; const char *what; } slots[5] = {{ch_x, n_x, "x"}, {ch_warped, C, "warped"}, {ch_flow, 2, "flow"},
+                                                         {ch_flow_norm, 1, "flow norm"}, {ch_diff_norm, 1, "diff norm"}};
+    for (int i = 0; i < 5; ++i) {
+        if (slots[i].ch < 0) continue;
+        if (slots[i].n < 0 || slots[i].ch + slots[i].n > cat_channels)
+            return fail(FN2B200_EINVAL, "warp_concat_forward: %s channels [%d, %d) outside the %d-channel output",
+                        slots[i].what, slots[i].ch, slots[i].ch + slots[i].n, cat_channels);
+        for (int j = 0; j < i; ++j)
+            if (slots[j].ch >= 0 && slots[i].ch < slots[j].ch + slots[j].n && slots[j].ch < slots[i].ch + slots[i].n)
+                return fail(FN2B200_EINVAL, "warp_concat_forward: %s and %s channel ranges overlap", slots[i].what, slots[j].what);
+    }
+    if (ch_x >= 0 && n_x > 2 * C) return fail(FN2B200_EINVAL, "warp_concat_forward: n_x=%d > 2C", n_x);
+    if (ch_flow >= 0 && flow_div == 0.f) return fail(FN2B200_EINVAL, "warp_concat_forward: flow_div = 0");
+    if ((int64_t)B * cat_channels * H * W >= (1LL << 31)) return fail(FN2B200_EINVAL, "warp_concat_forward: tensor exceeds 2^31 elements");
+    if (B == 0) return 0;
+    if (!x || !cat) return fail(FN2B200_ENULL, "warp_concat_forward: null pointer");
+    const float *img1 = x + (int64_t)C * xstride[1];          // x = [img0 | img1] along channels (models.py:124-126)
+    if ((rc = bind_device_of(flow))) return rc;
+    FlowSrc fs = {flow, fh, fw, upsample_mode, upsample_mode ? flow_mul : 1.f};
+    WarpOut o = {cat, cat_channels, ch_x, n_x, ch_warped, ch_flow, ch_flow_norm, ch_diff_norm, flow_div};
+    return resample2d_forward_tile(img1, xstride, x, xstride, fs, o, B, C, H, W, 1, (cudaStream_t)stream);
+}
+
+int fn2b200_resample2d_backward_ws(const float *img, const int64_t *istride, const float *flow,
+                                   const float *gout, float *gimg, float *gflow, int B, int C, int iH, int iW, int H,
+                                   int W, int kernel_size, int bilinear, int zero_grad_input1, void *workspace,
+                                   size_t workspace_bytes, void *stream);
 
 int fn2b200_resample2d_backward(const float *img, const int64_t *istride, const float *flow,
                                 const float *gout, float *gimg, float *gflow, int B, int C,
                                 int iH, int iW, int H, int W, int kernel_size, int bilinear,
                                 int zero_grad_input1, void *stream) {
+    return fn2b200_resample2d_backward_ws(img, istride, flow, gout, gimg, gflow, B, C, iH, iW, H, W, kernel_size, bilinear,
+                                          zero_grad_input1, nullptr, 0, stream);
+}
+
+size_t fn2b200_resample2d_backward_workspace(const int64_t *istride, int B, int C, int iH, int iW, int H, int W) {
+    if (!istride || B <= 0 || C <= 0 || C > 3 || H <= 0 || W <= 0) return 0;
+    (void)H; (void)W;
+    if (rs_family() == RS_TILE && rs_scatter() == 2) return resample2d_backward_workspace_bytes(B, iH, iW);
+    return 0;
+}
+
+int fn2b200_resample2d_backward_ws(const float *img, const int64_t *istride, const float *flow,
+                                   const float *gout, float *gimg, float *gflow, int B, int C, int iH, int iW, int H,
+                                   int W, int kernel_size, int bilinear, int zero_grad_input1, void *workspace,
+                                   size_t workspace_bytes, void *stream) {
     (void)bilinear;  // the reference's backward ignores it (resample2d_kernel.cu:75-198)
     int rc = check_resample("resample2d_backward", istride, B, C, iH, iW, H, W, kernel_size);
     if (rc) return rc;
     if (B == 0) return 0;
     if (!img || !flow || !gout) return fail(FN2B200_ENULL, "resample2d_backward: null pointer");
+    if (!gimg && !gflow) return 0;
     if ((rc = bind_device_of(flow))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (gimg && zero_grad_input1) {
+    const int fam = rs_family();
+    const bool ws_ok = workspace && workspace_bytes >= resample2d_backward_workspace_bytes(B, iH, iW) &&
+                       !(reinterpret_cast<uintptr_t>(workspace) & 15);
+    // zero_grad_input1 == 0: the caller zero-filled grad_input1 and expects accumulation into it (resample2d.py:31)
+    int scatter = fam == RS_ROW ? 1 : rs_scatter();
+    if (scatter == 2 && !(ws_ok && C <= 3)) scatter = 1;
+    if (gimg && zero_grad_input1 && scatter != 2) {          // scatter 2 overwrites grad_input1 from its scratch
         cudaError_t e = cudaMemsetAsync(gimg, 0, sizeof(float) * (size_t)B * C * iH * iW, st);
-        if (e != cudaSuccess)
-            return fail((int)e, "resample2d_backward: memset failed (%s)", cudaGetErrorString(e));
+        if (e != cudaSuccess) return fail((int)e, "resample2d_backward: memset failed (%s)", cudaGetErrorString(e));
     }
-    if (!gimg && !gflow) return 0;
-    return resample2d_backward(img, istride, flow, gout, gimg, gflow, B, C, iH, iW, H, W, st);
+    if (fam == RS_ROW) return resample2d_backward(img, istride, flow, gout, gimg, gflow, B, C, iH, iW, H, W, st);
+    return resample2d_backward_tile(img, istride, flow, gout, gimg, gflow, workspace, scatter, !zero_grad_input1, B, C, iH, iW,
+                                    H, W, st);
 }
 
 int fn2b200_channelnorm_forward(const float *in, float *out, int B, int C, int H, int W,

@@ -107,6 +107,12 @@ __device__ __forceinline__ void stg_stream4(float *p, float4 v) {
 __device__ __forceinline__ void red_add_f32(float *p, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+__device__ __forceinline__ void red_add_v2(float *p, float a, float b) {      // p 8-byte aligned
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {      // p 16-byte aligned
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 #endif  // __CUDACC__
 
 // ---- kernel launchers (one per .cu) -----------------------------------------------------------
@@ -122,11 +128,54 @@ int resample2d_backward(const float *img, const int64_t *istride, const float *f
                         const float *gout, float *gimg, float *gflow, int B, int C, int iH, int iW,
                         int H, int W, cudaStream_t st);
 
+// Where a kernel gets its flow from.  mode 0: a full-resolution [B,2,H,W] tensor.  mode 1 / 2: a quarter-resolution
+// [B,2,fh,fw] tensor (H = 4 fh, W = 4 fw) that is multiplied by `mul` and upsampled x4 on the fly --
+// bilinear with align_corners = False (nn.Upsample(scale_factor=4, mode='bilinear'), models.py:42,56: source index
+// 0.25 (i + 0.5) - 0.5 clamped at 0, second tap i0 + (i0 < n - 1)) or nearest (i >> 2; models.py:72-73) -- the
+// composition models.py:130,142,154,167 spells out as `upsample(flow2 * div_flow)`.
+struct FlowSrc {
+    const float *p;
+    int fh, fw;
+    int mode;
+    float mul;
+};
+
+
+// Where the tile forward kernel writes (resample2d_tile.cu).  `cat` is a [B, cat_channels, H, W] fp32 tensor; each
+// ch_* is the first channel of that product inside it, or -1 to skip the product:
+//   ch_x       n_x channels copied from x (img0's C channels, then img1's)        models.py:138 `x`
+//   ch_warped  C channels  img1 warped by the flow                               models.py:133
+//   ch_flow    2 channels  flow / flow_div                                       models.py:138 `flow / div_flow`
+//   ch_fnorm   1 channel   sqrt(dx^2 + dy^2) of the (upsampled) flow             models.py:155,166
+//   ch_dnorm   1 channel   sqrt(sum_c (img0 - warped)^2)                         models.py:134-135
+// Plain Resample2d forward = {cat = output, cat_channels = C, ch_warped = 0, everything else -1}.
+struct WarpOut {
+    float *cat;
+    int cat_channels;
+    int ch_x, n_x, ch_warped, ch_flow, ch_fnorm, ch_dnorm;
+    float flow_div;
+};
+// 2-D tile kernels (resample2d_tile.cu): any strides, any C; `scatter` = 1 planar scalar reductions, 2 vector reductions
+// into the pixel-interleaved scratch of resample2d_backward_workspace_bytes() (zero-filled inside the call, transposed
+// afterwards; C <= 3).
+int resample2d_forward_tile(const float *img1, const int64_t *is1, const float *img0, const int64_t *is0,
+                            const FlowSrc &fs, const WarpOut &o, int B, int C, int H, int W, int bilinear, cudaStream_t st);
+int resample2d_backward_tile(const float *img, const int64_t *istride, const float *flow, const float *gout, float *gimg,
+                             float *gflow, void *workspace, int scatter, int accumulate, int B, int C, int iH, int iW,
+                             int H, int W, cudaStream_t st);
+size_t resample2d_backward_workspace_bytes(int B, int iH, int iW);
+int resample2d_backward_finish(const float *T, float *gimg, int accumulate, int B, int C, int iH, int iW, cudaStream_t st);
+
 struct CorrParams {
     int B, C, H, W;        // inputs [B,C,H,W]
     int pad, k, md, s1, s2;
     int kr, dr, ds, D;     // kernel radius, displacement radius / size / count
     int oH, oW;            // output spatial dims
+    // forward output placement / epilogue (FlowNetC.py:86-92): sample n's D planes start at
+    // out + n * out_bstride (elements; D*oH*oW = a dense [B,D,oH,oW] tensor, larger = a channel range of a wider
+    // concat buffer), and v < 0 is multiplied by `leaky` (1 = no activation, 0.1 = nn.LeakyReLU(0.1)).
+    long out_bstride;
+    float leaky;
 };
 int corr_forward_generic(const float *in1, const float *in2, float *out, const CorrParams &p,
                          cudaStream_t st);

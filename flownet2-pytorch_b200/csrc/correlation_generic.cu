@@ -50,7 +50,9 @@ corr_fwd_generic_kernel(const float *__restrict__ in1, const float *__restrict__
             acc += (s0 + s1) + (s2 + s3);
         }
     }
-    out[idx] = acc / (float)(p.k * p.k * p.C);
+    float v = acc / (float)(p.k * p.k * p.C);
+    if (p.leaky != 1.f) v = v > 0.f ? v : v * p.leaky;
+    out[(long)n * p.out_bstride + ((long)tc * p.oH + oy) * p.oW + ox] = v;
 }
 
 // WHICH == 1: gradInput1 (other = input2); WHICH == 2: gradInput2 (other = input1).  stride1 == 1.

@@ -151,8 +151,8 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPIWARPS + 32 * (TC_MAXPROD - 1);
 __global__ void __launch_bounds__(TC_THREADS, 1)
 corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ CUtensorMap m1l,
                    const __grid_constant__ CUtensorMap m2h, const __grid_constant__ CUtensorMap m2l,
-                   float *__restrict__ out, int B, int C, int H, int W, int ntiles, int TC_BST, int hint,
-                   int nprod, long long *__restrict__ dbg) {
+                   float *__restrict__ out, long out_bstride, float leaky, int B, int C, int H, int W, int ntiles,
+                   int TC_BST, int hint, int nprod, long long *__restrict__ dbg) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Hc = H >> 1, Wc = W >> 1;
@@ -301,6 +301,7 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
         const float inv_nelems = 1.0f / (float)C;
         const long plane = (long)H * W;
         const bool s8 = px_t & 8, s4 = px_t & 4, s2 = px_t & 2, s1 = px_t & 1;
+        const bool act = leaky != 1.f;
         uint32_t acount = 0;
         TcSeg sg;
         for (int tn = blockIdx.x, w = w0; tc_next_seg(tn, w, full, w1, sg);) {
@@ -308,7 +309,7 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
             const TcTile T = tc_decode(sg.t, nxt, nyt);
             const int yc = T.yc0 + py_t, xc = T.xc0 + px_t;
             const bool pix_ok = (yc < Hc) && (xc < Wc);
-            float *obase = out + (long)T.n * (TC_DS * TC_DS) * plane + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
+            float *obase = out + (long)T.n * out_bstride + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
             for (int u = ua; u < ub; ++u, ++acount) {
                 const int ab = acount % TC_NACC;
                 const bool rec = dbg && blockIdx.x == 0 && acount < 64 && p == 0 && half == 0;
@@ -337,7 +338,11 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
                     if (pix_ok && tj >= 0 && tj < TC_DS) {
                         float *o = obase + (long)(tj * TC_DS) * plane;
 #pragma unroll
-                        for (int ti = 0; ti < TC_DS; ++ti) __stcs(o + ti * plane, r[ti] * inv_nelems);
+                        for (int ti = 0; ti < TC_DS; ++ti) {
+                            float v = r[ti] * inv_nelems;
+                            if (act) v = v > 0.f ? v : v * leaky;      // fused nn.LeakyReLU (FlowNetC.py:87), warp-uniform
+                            __stcs(o + ti * plane, v);
+                        }
                     }
                 }
                 tcgen05_fence_before();
@@ -769,8 +774,8 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrPa
     while (nprod & (nprod - 1)) --nprod;          // power of two
     long long *dbg = nullptr;          // FN2B200_TC_DBG = device pointer: per-unit clock64 timeline of CTA 0 (tools/tc_timeline.py)
     if (const char *ev = getenv("FN2B200_TC_DBG")) dbg = reinterpret_cast<long long *>(strtoull(ev, nullptr, 0));
-    corr_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(m1h, m1l, m2h, m2l, out, p.B, p.C, p.H, p.W, ntiles, bst, hint, nprod,
-                                                        dbg);
+    corr_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(m1h, m1l, m2h, m2l, out, p.out_bstride, p.leaky, p.B, p.C, p.H, p.W,
+                                                        ntiles, bst, hint, nprod, dbg);
     count_launch();
     return check_launch("correlation_forward(tc)");
 }

@@ -156,12 +156,17 @@ corr_fwd_tiled_kernel(const __grid_constant__ CUtensorMap map1,
         const float nelems = (float)(p.k * p.k * p.C);
         const int ox = x0 + kPX * xb;
         const long plane = (long)p.oH * p.oW;
-        float *o = out + (((long)n * p.D + (long)(tj + DR) * DS) * p.oH + oy) * p.oW + ox;
+        float *o = out + (long)n * p.out_bstride + (((long)(tj + DR) * DS) * p.oH + oy) * p.oW + ox;
+        const float slope = p.leaky;          // 1 = no activation; otherwise nn.LeakyReLU(slope) (FlowNetC.py:87)
+        auto fin = [nelems, slope](float a) {
+            const float v = a / nelems;
+            return v > 0.f ? v : v * slope;    // v * 1 == v bit for bit
+        };
         if ((p.oW & 3) == 0 && ox + kPX <= p.oW) {
 #pragma unroll
             for (int t = 0; t < DS; ++t) {
-                float4 v0 = make_float4(acc[0][t] / nelems, acc[1][t] / nelems, acc[2][t] / nelems, acc[3][t] / nelems);
-                float4 v1 = make_float4(acc[4][t] / nelems, acc[5][t] / nelems, acc[6][t] / nelems, acc[7][t] / nelems);
+                float4 v0 = make_float4(fin(acc[0][t]), fin(acc[1][t]), fin(acc[2][t]), fin(acc[3][t]));
+                float4 v1 = make_float4(fin(acc[4][t]), fin(acc[5][t]), fin(acc[6][t]), fin(acc[7][t]));
                 stg_stream4(o + t * plane, v0);
                 stg_stream4(o + t * plane + 4, v1);
             }
@@ -170,7 +175,7 @@ corr_fwd_tiled_kernel(const __grid_constant__ CUtensorMap map1,
             for (int t = 0; t < DS; ++t)
 #pragma unroll
                 for (int i = 0; i < kPX; ++i)
-                    if (ox + i < p.oW) o[t * plane + i] = acc[i][t] / nelems;
+                    if (ox + i < p.oW) o[t * plane + i] = fin(acc[i][t]);
         }
     }
 }
@@ -398,6 +403,8 @@ static int launch_bwd(const float *other, const float *gout, float *gin, const C
 
 int corr_forward_tiled(const float *in1, const float *in2, float *out, const CorrParams &p,
                        cudaStream_t st) {
+    // the epilogue's st.global.v4 needs 16-byte aligned output rows: base, batch stride and plane size
+    if (!aligned16(out) || (p.out_bstride & 3)) return corr_forward_generic(in1, in2, out, p, st);
     if (!aligned16(in1) || !aligned16(in2))
         return corr_forward_generic(in1, in2, out, p, st);
 #define X(S2_, DR_) if (p.s2 == S2_ && p.dr == DR_) return launch_fwd<S2_, DR_>(in1, in2, out, p, st);

@@ -13,24 +13,12 @@
 // Backward: a single fused kernel computes both flow-gradient channels per thread (the reference
 // runs 2 threads that each redo the 4*C gathers) and scatters the image gradient with
 // red.global.add.f32 (no return value -> no round trip).
-#include "common.cuh"
+//
+// Round 2: these row kernels (one CTA = 256 consecutive pixels of one row) are kept as the comparison point
+// (FN2B200_RESAMPLE=row); the shipped kernels are the 2-D tile kernels of resample2d_tile.cu.
+#include "resample_common.cuh"
 
 namespace fn2 {
-
-struct Taps {
-    int xL, xR, yT, yB;
-};
-
-__device__ __forceinline__ Taps clamp_taps(float fx, float fy, int W, int H) {
-    // fx = floor(xf), fy = floor(yf).  int(floor(xf)+1): the +1 is done in float like the
-    // reference (resample2d_kernel.cu:49-52); cvt.rzi saturates for huge |xf|.
-    Taps t;
-    t.xL = max(min((int)fx, W - 1), 0);
-    t.xR = max(min((int)(fx + 1.0f), W - 1), 0);
-    t.yT = max(min((int)fy, H - 1), 0);
-    t.yB = max(min((int)(fy + 1.0f), H - 1), 0);
-    return t;
-}
 
 template <int CT>
 __global__ void __launch_bounds__(256)
@@ -61,20 +49,20 @@ resample2d_fwd(const float *__restrict__ img, long sb, long sc, long sh, long sw
         for (int c = 0; c < (CT > 0 ? CT : 1); ++c) {
             if (CT > 0) {
                 const float *ic = ib + c * sc;
-                float v = w00 * __ldg(ic + oTL);  // same term order as the reference (:56-59)
-                v += w01 * __ldg(ic + oTR);
-                v += w10 * __ldg(ic + oBL);
-                v += w11 * __ldg(ic + oBR);
+                float v = __fmul_rn(w00, __ldg(ic + oTL));  // same term order as the reference (:56-59)
+                v = __fmaf_rn(w01, __ldg(ic + oTR), v);
+                v = __fmaf_rn(w10, __ldg(ic + oBL), v);
+                v = __fmaf_rn(w11, __ldg(ic + oBR), v);
                 __stcs(ob + (long)c * hw, v);
             }
         }
         if (CT == 0) {
             for (int c = 0; c < Cn; ++c) {
                 const float *ic = ib + c * sc;
-                float v = w00 * __ldg(ic + oTL);
-                v += w01 * __ldg(ic + oTR);
-                v += w10 * __ldg(ic + oBL);
-                v += w11 * __ldg(ic + oBR);
+                float v = __fmul_rn(w00, __ldg(ic + oTL));
+                v = __fmaf_rn(w01, __ldg(ic + oTR), v);
+                v = __fmaf_rn(w10, __ldg(ic + oBL), v);
+                v = __fmaf_rn(w11, __ldg(ic + oBR), v);
                 __stcs(ob + (long)c * hw, v);
             }
         }

@@ -14,15 +14,25 @@ class HostPipeline(object):
 
     compute(dev_in, dev_out) is called on the pipeline's compute stream with lists of device tensors; it must
     only enqueue work on the current stream (our layers and the reference's do).  host_in / host_out are
-    sequences of pinned CPU tensors of the declared shapes.  submit() returns immediately; drain() makes the
-    caller's current stream wait for everything submitted so far."""
+    sequences of pinned CPU tensors of the declared shapes.  submit() returns immediately.
 
-    def __init__(self, in_shapes, out_shapes, device, depth=2, dtype=torch.float32):
+    Host-buffer lifetime: a host_in tensor must not be overwritten, and a host_out tensor must not be read, until
+    the step that uses it has left the pipeline -- i.e. after drain() (which by default blocks the calling thread until
+    the last D2H copy has landed) or after ``depth`` further submit() calls followed by drain(host_sync=False) plus
+    a synchronisation of the caller's stream.  Pass ``numa_bind=True`` (one process per GPU) to pin the process to the
+    GPU's NUMA node first, so that pinned buffers allocated AFTERWARDS sit behind the GPU's own PCIe root."""
+
+    def __init__(self, in_shapes, out_shapes, device, depth=2, dtype=torch.float32, numa_bind=False):
         if depth < 1:
             raise ValueError("HostPipeline: depth must be >= 1")
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("HostPipeline needs a CUDA device (there is no CPU path)")
+        self.numa = None
+        if numa_bind:
+            from . import numa
+            idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            self.numa = numa.bind_to_device_node(idx)
         self.depth = depth
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
         self.dev_in = [[torch.empty(tuple(s), device=self.device, dtype=dtype) for s in in_shapes] for _ in range(depth)]
@@ -59,8 +69,12 @@ class HostPipeline(object):
                 h.copy_(d, non_blocking=True)
             self.ev_out[s].record(self.s_out)
 
-    def drain(self):
+    def drain(self, host_sync=True):
+        """Make the caller's current stream wait for everything submitted so far; with host_sync (default) also block
+        the calling thread until the last D2H copy has completed, so host_out can be read and host_in reused."""
         cur = torch.cuda.current_stream(self.device)
         cur.wait_stream(self.s_in)
         cur.wait_stream(self.s_comp)
         cur.wait_stream(self.s_out)
+        if host_sync and self.count:
+            self.ev_out[(self.count - 1) % self.depth].synchronize()

@@ -39,6 +39,7 @@
 #ifndef FN2B200_H_
 #define FN2B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -88,6 +89,18 @@ int fn2b200_correlation_forward_ws(const float *input1, const float *input2, flo
                                    size_t workspace_bytes, void *stream);
 
 /*
+ * SURVEY 8(f)-2 (FlowNetC.py:86-92): the forward writing LeakyReLU(leaky_slope)(correlation) straight into channels
+ * [ch_offset, ch_offset + D) of a [B, cat_channels, oH, oW] concat buffer (FlowNetC: 473 channels, conv_redir's 32
+ * first, then the 441 displacement channels), so that neither the activation's read-modify-write nor torch.cat's copy
+ * of the cost volume happens.  leaky_slope = 1 writes the plain correlation.  workspace as in
+ * fn2b200_correlation_forward_ws (NULL -> FP32-FMA kernels).  The other channels of `cat` are not touched.
+ */
+int fn2b200_correlation_forward_cat(const float *input1, const float *input2, float *cat, int cat_channels,
+                                    int ch_offset, float leaky_slope, int B, int C, int H, int W, int pad_size,
+                                    int kernel_size, int max_displacement, int stride1, int stride2,
+                                    int corr_type_multiply, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
  * Tensor-core backward, same workspace size and layout as the forward's.  workspace_has_split != 0
  * promises that the workspace still holds what fn2b200_correlation_forward_ws wrote for the SAME
  * input1/input2 (the split pass is then skipped).  FN2B200_CORR_BWD=fma forces the FMA kernels.
@@ -133,6 +146,51 @@ int fn2b200_resample2d_backward(const float *input1, const int64_t *istride, con
                                 const float *grad_output, float *grad_input1, float *grad_input2,
                                 int B, int C, int iH, int iW, int H, int W, int kernel_size,
                                 int bilinear, int zero_grad_input1, void *stream);
+
+/*
+ * Backward with a caller-provided scratch: fn2b200_resample2d_backward_workspace() returns the bytes needed (0 = C > 3
+ * or FN2B200_RS_BWD=planar: scalar reductions straight into grad_input1, what fn2b200_resample2d_backward does), and
+ * fn2b200_resample2d_backward_ws() is fn2b200_resample2d_backward() plus a 16-byte aligned device workspace of at least
+ * that size (NULL is fine when grad_input1 is NULL).  The image gradient is accumulated in the workspace as ONE
+ * 16-byte vector reduction per bilinear tap (pixel-interleaved layout [B][iH][iW][4]: 4 lane-operations per pixel
+ * instead of 4 C) and transposed into grad_input1 afterwards: grad_input1 then needs no zero fill; with
+ * zero_grad_input1 == 0 the result is ADDED to what it holds.
+ */
+size_t fn2b200_resample2d_backward_workspace(const int64_t *istride, int B, int C, int iH, int iW, int H, int W);
+int fn2b200_resample2d_backward_ws(const float *input1, const int64_t *istride, const float *input2,
+                                   const float *grad_output, float *grad_input1, float *grad_input2, int B, int C,
+                                   int iH, int iW, int H, int W, int kernel_size, int bilinear, int zero_grad_input1,
+                                   void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Resample2d whose flow is still at quarter resolution.  output = Resample2d()(input1, up(flow * flow_mul))
+ * where up = nn.Upsample(scale_factor=4, mode='bilinear') (upsample_mode 1; align_corners=False arithmetic) or
+ * mode='nearest' (upsample_mode 2) -- the chain the reference spells out at models.py:130-133, :142-145, :154-157,
+ * :167-168 -- without the full-resolution flow ever being written.  flow: [B,2,fh,fw] contiguous with H = 4 fh,
+ * W = 4 fw (upsample_mode 0: fh = H, fw = W, flow_mul ignored).  input1 as in fn2b200_resample2d_forward (any
+ * element strides, any C) with iH = H, iW = W.
+ */
+int fn2b200_resample2d_forward_up(const float *input1, const int64_t *istride, const float *flow, int fh, int fw,
+                                  int upsample_mode, float flow_mul, float *output, int B, int C, int H, int W,
+                                  void *stream);
+
+/*
+ * warp -> diff -> channel-norm -> concat in one kernel (models.py:133-138, :145-150, :155-161, :168-174).
+ * x: [B, >= 2C, H, W] with element strides xstride[4] (unit stride along W), img0 = x[:, :C], img1 = x[:, C:2C].
+ * flow / fh / fw / upsample_mode / flow_mul: as in fn2b200_resample2d_forward_up (flow_up below is the upsampled flow).
+ * cat: [B, cat_channels, H, W] contiguous; each ch_* names the first channel of one product, negative = not wanted:
+ *   ch_x         n_x channels      x[:, :n_x]                                  (n_x <= 2C)
+ *   ch_warped    C channels        warped = Resample2d()(img1, flow_up)
+ *   ch_flow      2 channels        flow_up / flow_div
+ *   ch_flow_norm 1 channel         ChannelNorm()(flow_up)
+ *   ch_diff_norm 1 channel         ChannelNorm()(img0 - warped)
+ * Channel ranges must not overlap; channels no product covers are left untouched.  models.py:138's concat1 is {cat_channels 12, ch_x 0, n_x 6, ch_warped 6, ch_flow 9,
+ * flow_div = div_flow, ch_flow_norm -1, ch_diff_norm 11}.
+ */
+int fn2b200_warp_concat_forward(const float *x, const int64_t *xstride, int C, const float *flow, int fh, int fw,
+                                int upsample_mode, float flow_mul, float *cat, int cat_channels, int ch_x, int n_x,
+                                int ch_warped, int ch_flow, float flow_div, int ch_flow_norm, int ch_diff_norm, int B,
+                                int H, int W, void *stream);
 
 /* input1: [B,C,H,W]; output: [B,1,H,W] = sqrt(sum_c x^2).  norm_deg is ignored (reference: same). */
 int fn2b200_channelnorm_forward(const float *input1, float *output, int B, int C, int H, int W,

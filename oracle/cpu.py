@@ -157,3 +157,53 @@ def channelnorm_backward(input1, output, grad_output, norm_deg=2):
     gi = np.zeros_like(a)
     lib().orc_channelnorm_backward(pa, po, pg, gi.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), B, C, H, W)
     return gi
+
+
+def upsample4(planes, mode, mul=1.0):
+    """[B,C,h,w] -> [B,C,4h,4w]; mode 1 = nn.Upsample(scale_factor=4, mode='bilinear'), 2 = 'nearest'; every input
+    value is multiplied by ``mul`` first (models.py:130 ``upsample1(flow2 * div_flow)``)."""
+    a, pa = _f(planes)
+    B, C, h, w = a.shape
+    out = np.zeros((B, C, 4 * h, 4 * w), np.float32)
+    L = lib()
+    L.orc_upsample4.argtypes = [ctypes.POINTER(ctypes.c_float)] * 2 + [ctypes.c_int] * 4 + [ctypes.c_float]
+    rc = L.orc_upsample4(pa, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), B * C, h, w, int(mode), float(mul))
+    if rc:
+        raise ValueError("oracle upsample4: mode must be 1 (bilinear) or 2 (nearest)")
+    return out
+
+
+def warp_concat_forward(x, flow, C=3, upsample_mode=0, flow_mul=1.0, cat_channels=None, ch_x=0, n_x=None, ch_warped=None,
+                        ch_flow=None, flow_div=1.0, ch_flow_norm=-1, ch_diff_norm=None):
+    """The chain models.py:130-138 (and :142-150, :154-161, :167-174) builds from nn.Upsample, Resample2d, a
+    subtraction, ChannelNorm, a division and torch.cat -- composed from the oracle's own ops, one array out:
+
+        flow_up   = upsample4(flow * flow_mul)                 (or flow itself when upsample_mode == 0)
+        warped    = resample2d(x[:, C:2C], flow_up)
+        diff_norm = channelnorm(x[:, :C] - warped)
+        cat[:, ch_x : ch_x + n_x] = x[:, :n_x];  cat[:, ch_warped ...] = warped;  cat[:, ch_flow ...] = flow_up / flow_div
+        cat[:, ch_flow_norm] = channelnorm(flow_up);  cat[:, ch_diff_norm] = diff_norm
+
+    Defaults give models.py:138's 12-channel layout (x | warped | flow / div_flow | diff norm).  Channels that no
+    product is assigned to stay 0.  A negative ch_* skips that product."""
+    x = np.ascontiguousarray(x, np.float32)
+    n_x = 2 * C if n_x is None else n_x
+    ch_warped = 2 * C if ch_warped is None else ch_warped
+    ch_flow = 3 * C if ch_flow is None else ch_flow
+    ch_diff_norm = 3 * C + 2 if ch_diff_norm is None else ch_diff_norm
+    cat_channels = 3 * C + 3 if cat_channels is None else cat_channels
+    flow_up = upsample4(flow, upsample_mode, flow_mul) if upsample_mode else np.ascontiguousarray(flow, np.float32)
+    B, _, H, W = flow_up.shape
+    warped = resample2d_forward(x[:, C:2 * C], flow_up)
+    cat = np.zeros((B, cat_channels, H, W), np.float32)
+    if ch_x >= 0:
+        cat[:, ch_x:ch_x + n_x] = x[:, :n_x]
+    if ch_warped >= 0:
+        cat[:, ch_warped:ch_warped + C] = warped
+    if ch_flow >= 0:
+        cat[:, ch_flow:ch_flow + 2] = flow_up / np.float32(flow_div)
+    if ch_flow_norm >= 0:
+        cat[:, ch_flow_norm:ch_flow_norm + 1] = channelnorm_forward(flow_up)
+    if ch_diff_norm >= 0:
+        cat[:, ch_diff_norm:ch_diff_norm + 1] = channelnorm_forward(x[:, :C] - warped)
+    return cat

@@ -261,6 +261,125 @@ def test_resample2d_vs_oracle(shape, sigma, C):
     assert_close(g2.cpu().numpy(), r2, TOL, "resample gFlow")
 
 
+@pytest.mark.parametrize("shape,sigma,C", [((2, 40, 72), 4.0, 3), ((1, 33, 52), 64.0, 3), ((2, 64, 128), 2.0, 2),
+                                           ((1, 70, 200), 9.0, 1), ((1, 36, 64), 30.0, 3), ((1, 96, 256), 0.3, 3),
+                                           ((1, 21, 45), 5.0, 5), ((2, 19, 30), 3.0, 3)])
+def test_resample2d_kernel_families_vs_oracle(shape, sigma, C, monkeypatch):
+    """Every Resample2d kernel family on the same inputs: 2-D tiles (default; PY = 1, 2, 4 rows per thread; both scatter
+    flavours of the backward: vector reductions into the interleaved scratch, planar scalar reductions) and round 1's
+    row kernels; partial tiles on both axes, C = 1, 2, 3 and the runtime-C path (5).
+    Forward and flow gradient must agree bit for bit across families (same arithmetic); the image gradient (atomic
+    order differs) within 1e-5; everything against the oracle within the 1e-4 contract."""
+    f = _f2()
+    F2 = f.functional
+    B, H, W = shape
+    g = torch.Generator().manual_seed(23)
+    img = torch.rand(B, C, H, W, generator=g)
+    flow = torch.randn(B, 2, H, W, generator=g) * sigma
+    go = torch.randn(B, C, H, W, generator=g)
+    imd, fld, god = img.cuda(), flow.cuda(), go.cuda()
+    ref = orc.resample2d_forward(img.numpy(), flow.numpy())
+    r1, r2 = orc.resample2d_backward(img.numpy(), flow.numpy(), go.numpy())
+    huge = flow.clone()
+    huge[0, :, 0, 0] = float("nan")                      # NaN flow: taps clamp to (0, 0), NaN weights -> NaN out, no fault
+    huge[0, 0, 1, 1] = 3e9                               # saturating float->int conversion (UB in the C oracle)
+    huge[0, 1, 2, 2] = -float("inf")
+    hud = huge.cuda()
+    base = {}
+    envs = [("tile", {}), ("tile py1", {"FN2B200_RS_PY": "1"}), ("tile py2 planar", {"FN2B200_RS_PY": "2", "FN2B200_RS_BWD": "planar"}),
+            ("tile py4 planar", {"FN2B200_RS_BWD": "planar"}), ("row", {"FN2B200_RESAMPLE": "row"})]
+    for name, env in envs:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = F2.resample2d_forward(imd, fld)
+        g1, g2 = F2.resample2d_backward(imd, fld, god)
+        of = F2.resample2d_backward(imd, fld, god, need1=False)
+        oi = F2.resample2d_backward(imd, fld, god, need2=False)
+        oh = torch.nan_to_num(F2.resample2d_forward(imd, hud), nan=-1.0)
+        for k in env:
+            monkeypatch.delenv(k)
+        assert_close(out.cpu().numpy(), ref, TOL, name + ": resample fwd")
+        assert_close(g1.cpu().numpy(), r1, TOL, name + ": resample gImg")
+        assert_close(g2.cpu().numpy(), r2, TOL, name + ": resample gFlow")
+        assert of[0] is None and torch.equal(of[1], g2), name
+        assert oi[1] is None
+        assert_close(oi[0].cpu().numpy(), r1, TOL, name + ": resample gImg only")
+        if not base:
+            base = dict(out=out, g1=g1, g2=g2, oh=oh)
+            assert bool((oh[0, :, 0, 0] == -1.0).all())
+        else:
+            d = (out - base["out"]).abs().max().item()
+            assert torch.equal(out, base["out"]), "%s: forward differs from the tile kernel by %.3e" % (name, d)
+            assert torch.equal(g2, base["g2"]), name + ": flow gradient differs"
+            assert torch.equal(oh, base["oh"]), name + ": NaN / inf / huge flows handled differently"
+            assert_close(g1.cpu().numpy(), base["g1"].cpu().numpy(), 1e-5, name + ": image gradient vs tile kernel")
+
+
+def test_resample2d_shim_accumulates_into_caller_zeroed_gradient():
+    """B1 convention (resample2d.py:31-32): gradInput1 arrives zero-filled and the kernel accumulates into it."""
+    f = _f2()
+    g = torch.Generator().manual_seed(24)
+    img, flow = torch.rand(1, 3, 32, 64, generator=g).cuda(), (torch.randn(1, 2, 32, 64, generator=g) * 3).cuda()
+    go = torch.randn(1, 3, 32, 64, generator=g).cuda()
+    base = torch.full_like(img, 0.5)
+    g1, _ = f.functional.resample2d_backward(img, flow, go, out1=base.clone(), zero_out1=False)
+    ref, _ = f.functional.resample2d_backward(img, flow, go)
+    assert_close((g1 - 0.5).cpu().numpy(), ref.cpu().numpy(), 1e-5, "accumulate into caller buffer")
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+def test_resample2d_with_fused_flow_upsample(mode):
+    """SURVEY 8(f)-3 (models.py:130-133): Resample2d reading a quarter-resolution flow; against the oracle's
+    upsample4 + resample2d composition and against torch's nn.Upsample feeding our own Resample2d."""
+    f = _f2()
+    g = torch.Generator().manual_seed(25)
+    img = torch.rand(2, 3, 48, 80, generator=g)
+    lr = torch.randn(2, 2, 12, 20, generator=g) * 0.4
+    out = f.functional.resample2d_forward_up(img.cuda(), lr.cuda(), mode, 20.0)
+    up = orc.upsample4(lr.numpy(), 1 if mode == "bilinear" else 2, 20.0)
+    assert_close(out.cpu().numpy(), orc.resample2d_forward(img.numpy(), up), TOL, "resample_up vs oracle")
+    t_up = torch.nn.Upsample(scale_factor=4, mode=mode)(lr.cuda() * 20.0)
+    assert_close(out.cpu().numpy(), f.functional.resample2d_forward(img.cuda(), t_up).cpu().numpy(), TOL, "resample_up vs torch upsample")
+    with pytest.raises(RuntimeError, match="does not match"):
+        f.functional.resample2d_forward_up(img.cuda(), lr[:, :, :11].contiguous().cuda(), mode, 20.0)
+
+
+def test_warp_concat_forward_vs_oracle_composition():
+    """SURVEY 8(f)-1 (models.py:130-138): one kernel for upsample -> warp -> diff -> channel-norm -> concat."""
+    f = _f2()
+    g = torch.Generator().manual_seed(26)
+    x = torch.rand(2, 6, 48, 80, generator=g) - 0.5
+    flow = torch.randn(2, 2, 48, 80, generator=g) * 5
+    cat = f.functional.warp_concat_forward(x.cuda(), flow.cuda(), flow_div=20.0)
+    assert cat.shape == (2, 12, 48, 80)
+    ref = orc.warp_concat_forward(x.numpy(), flow.numpy(), flow_div=20.0)
+    assert np.array_equal(cat[:, :6].cpu().numpy(), x.numpy())
+    assert_close(cat.cpu().numpy(), ref, TOL, "warp_concat (models.py:138 layout)")
+    for c0, c1, what in ((6, 9, "warped"), (9, 11, "flow/div"), (11, 12, "diff norm")):
+        assert_close(cat[:, c0:c1].cpu().numpy(), ref[:, c0:c1], TOL, "warp_concat " + what)
+    # the fusion-stage layout (models.py:154-174): quarter-resolution flow, nearest upsample, x / div_flow folded in,
+    # flow + flow norm + diff norm into chosen channels of an 11-channel buffer; img0 copied, warped not written
+    lr = torch.randn(2, 2, 12, 20, generator=g) * 8
+    buf = torch.full((2, 11, 48, 80), 7.0).cuda()
+    f.functional.warp_concat_forward(x.cuda(), lr.cuda(), upsample="nearest", flow_mul=1.0 / 20.0, out=buf, ch_x=0, n_x=3,
+                                     ch_warped=-1, ch_flow=3, flow_div=1.0, ch_flow_norm=7, ch_diff_norm=9)
+    ref = orc.warp_concat_forward(x.numpy(), lr.numpy(), upsample_mode=2, flow_mul=1.0 / 20.0, cat_channels=11, ch_x=0, n_x=3,
+                                  ch_warped=-1, ch_flow=3, flow_div=1.0, ch_flow_norm=7, ch_diff_norm=9)
+    got = buf.cpu().numpy()
+    for ch in (5, 6, 8, 10):
+        assert (got[:, ch] == 7.0).all()                  # channels nobody owns are left alone
+        ref[:, ch] = 7.0
+    assert_close(got, ref, TOL, "warp_concat fusion-stage layout")
+    # strided x (a channel slice of a larger tensor) and the bilinear-upsample variant
+    big = torch.rand(2, 8, 48, 80, generator=g).cuda()
+    xs = big[:, 1:7]
+    cat = f.functional.warp_concat_forward(xs, lr.cuda(), upsample="bilinear", flow_mul=20.0, flow_div=20.0)
+    ref = orc.warp_concat_forward(xs.cpu().numpy(), lr.numpy(), upsample_mode=1, flow_mul=20.0, flow_div=20.0)
+    assert_close(cat.cpu().numpy(), ref, TOL, "warp_concat strided x + bilinear upsample")
+    with pytest.raises(RuntimeError, match="overlap"):
+        f.functional.warp_concat_forward(x.cuda(), flow.cuda(), ch_warped=4)
+
+
 def test_resample2d_strided_image_slice_and_module():
     """FlowNet2 passes x[:,3:,:,:] (non-contiguous, models.py:133); no .contiguous() copy needed."""
     f = _f2()
@@ -307,6 +426,45 @@ def test_resample2d_full_size_properties():
     assert abs(float(g1.double().sum()) - float(go.double().sum())) < 1e-3 * float(go.double().abs().sum()) ** 0.5 + 1.0
 
 
+def test_resample2d_full_size_sigma64_border_clamps():
+    """cfg3 with sigma = 64 px: more than half of the taps clamp to the border; fwd and bwd vs oracle."""
+    f = _f2()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    img = torch.rand(8, 3, 448, 1024, device="cuda", generator=g)
+    flow = torch.randn(8, 2, 448, 1024, device="cuda", generator=g) * 64
+    go = torch.randn(8, 3, 448, 1024, device="cuda", generator=g)
+    xf = torch.arange(1024, device="cuda").view(1, 1, 1024) + flow[:, 0]
+    yf = torch.arange(448, device="cuda").view(1, 448, 1) + flow[:, 1]
+    oob = ((xf < 0) | (xf > 1023) | (yf < 0) | (yf > 447)).float().mean().item()
+    assert oob > 0.15, oob
+    out = f.functional.resample2d_forward(img, flow)
+    g1, g2 = f.functional.resample2d_backward(img, flow, go)
+    n = 6
+    i_, f_, g_ = img[n:n + 1].cpu().numpy(), flow[n:n + 1].cpu().numpy(), go[n:n + 1].cpu().numpy()
+    assert_close(out[n:n + 1].cpu().numpy(), orc.resample2d_forward(i_, f_), TOL, "cfg3 sigma64 fwd")
+    r1, r2 = orc.resample2d_backward(i_, f_, g_)
+    assert_close(g1[n:n + 1].cpu().numpy(), r1, TOL, "cfg3 sigma64 gImg")
+    assert_close(g2[n:n + 1].cpu().numpy(), r2, TOL, "cfg3 sigma64 gFlow")
+    assert abs(float(g1.double().sum()) - float(go.double().sum())) < 1e-3 * float(go.double().abs().sum()) ** 0.5 + 1.0
+
+
+def test_warp_concat_full_size():
+    """[8,6,448,1024] + quarter-resolution flow: one sample against the oracle composition (models.py:130-138)."""
+    f = _f2()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.rand(8, 6, 448, 1024, device="cuda", generator=g) - 0.5
+    lr = torch.randn(8, 2, 112, 256, device="cuda", generator=g) * 0.3
+    cat = f.functional.warp_concat_forward(x, lr, upsample="bilinear", flow_mul=20.0, flow_div=20.0)
+    n = 4
+    ref = orc.warp_concat_forward(x[n:n + 1].cpu().numpy(), lr[n:n + 1].cpu().numpy(), upsample_mode=1, flow_mul=20.0, flow_div=20.0)
+    assert_close(cat[n:n + 1].cpu().numpy(), ref, TOL, "warp_concat full size")
+    # unfused chain through the individual modules gives the same tensor
+    up = torch.nn.Upsample(scale_factor=4, mode="bilinear")(lr * 20.0)
+    warped = f.Resample2d()(x[:, 3:], up)
+    chain = torch.cat((x, warped, up / 20.0, f.ChannelNorm()(x[:, :3] - warped)), dim=1)
+    assert rel_err(cat.cpu().numpy(), chain.cpu().numpy()) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------
 # ChannelNorm
 # ------------------------------------------------------------------------------------------------
@@ -351,7 +509,6 @@ def test_channelnorm_16bit_native(dtype, shape):
 needs_ref = pytest.mark.skipif(not oref.available(), reason="oracle/_ref reference extensions not built")
 
 
-@needs_ref
 def test_host_pipeline_matches_resident_results():
     """flownet2_b200.hostpipe.HostPipeline: 5 steps with different host inputs through 2 buffer slots give, for
     every step, exactly what the resident call gives (stream / event ordering of slot reuse)."""
@@ -383,6 +540,7 @@ def test_host_pipeline_matches_resident_results():
         pipe.submit(compute, [torch.empty(shape)] * 2 + [torch.empty(oshape)], steps[0][1])   # not pinned
 
 
+@needs_ref
 @pytest.mark.parametrize("shape", [(1, 256, 48, 64), (2, 20, 13, 36)])
 def test_correlation_vs_reference_kernels(shape):
     f = _f2()
@@ -477,3 +635,80 @@ def test_unmodified_reference_models_run_on_our_layers(name):
     assert np.isfinite(outs["ref"]).all()
     assert rel_err(outs["B1"], outs["ref"]) < 1e-3, rel_err(outs["B1"], outs["ref"])
     assert rel_err(outs["B2"], outs["ref"]) < 1e-3, rel_err(outs["B2"], outs["ref"])
+
+
+@needs_models
+@pytest.mark.parametrize("name", ["FlowNet2C", "FlowNet2"])
+def test_full_size_output_flow_agreement(name):
+    """SURVEY 8(d) cfg4 / cfg5 at the stated configuration: 448x1024, bs 8, random xavier weights (seed 0), U(0,255)
+    input, deterministic cuDNN with TF32 off -- the output flow of the unmodified models.py on our layers (B2) and
+    through the fused forwards (flownet2_b200.fused) against the same network on the reference's own kernels."""
+    from flownet2_b200 import compat, fused
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(8, 3, 2, 448, 1024, generator=g) * 255.0).cuda()
+    net = _build_ref_model(name, "ref")
+    with torch.no_grad():
+        ref = net(x).float().cpu().numpy()
+    del net
+    torch.cuda.empty_cache()
+    net = _build_ref_model(name, "B2")
+    n0 = _f2().functional.launch_count()
+    with torch.no_grad():
+        ours = net(x).float().cpu().numpy()
+    n1 = _f2().functional.launch_count()
+    fz = fused.fused_forward(net, x).float().cpu().numpy()
+    n2 = _f2().functional.launch_count()
+    del net
+    compat.uninstall()
+    torch.cuda.empty_cache()
+    assert ref.shape == (8, 2, 448, 1024) and np.isfinite(ref).all()
+    assert n1 > n0 and 0 < n2 - n1 < n1 - n0 or name == "FlowNet2C"      # the fused graph launches fewer of our kernels
+    assert rel_err(ours, ref) < 1e-3, rel_err(ours, ref)
+    assert rel_err(fz, ref) < 1e-3, rel_err(fz, ref)
+    assert rel_err(fz, ours) < 1e-3, rel_err(fz, ours)
+
+
+def test_correlation_forward_cat_leaky_epilogue():
+    """SURVEY 8(f)-2 (FlowNetC.py:86-92): LeakyReLU(0.1)(corr) written into channels 32.. of a 473-channel buffer,
+    on all three kernel families, against torch's cat(leaky_relu(our plain forward)) and the oracle."""
+    f = _f2()
+    for shape, prm in (((2, 64, 12, 20), (20, 1, 20, 1, 2)),        # tensor cores
+                       ((1, 20, 13, 64), (20, 1, 20, 1, 2)),        # TMA-tiled FMA
+                       ((1, 6, 10, 12), (4, 3, 4, 1, 2))):          # generic
+        a, b = _randn(shape, 80).cuda(), _randn(shape, 81).cuda()
+        D, oH, oW = f.functional.correlation_out_shape(shape[1], shape[2], shape[3], *prm)
+        cat = torch.full((shape[0], 32 + D + 3, oH, oW), 5.0).cuda()
+        f.functional.correlation_forward_cat(a, b, cat, 32, 0.1, *prm)
+        plain = f.functional.correlation_forward(a, b, *prm)
+        assert torch.equal(cat[:, 32:32 + D], torch.nn.functional.leaky_relu(plain, 0.1))
+        assert (cat[:, :32] == 5.0).all() and (cat[:, 32 + D:] == 5.0).all()
+        ref = orc.correlation_forward(a.cpu().numpy(), b.cpu().numpy(), *prm)
+        assert_close(cat[:, 32:32 + D].cpu().numpy(), np.where(ref > 0, ref, ref * np.float32(0.1)), TOL, "corr cat leaky")
+        cat2 = torch.empty((shape[0], D, oH, oW)).cuda()
+        f.functional.correlation_forward_cat(a, b, cat2, 0, 1.0, *prm)
+        assert torch.equal(cat2, plain)
+    with pytest.raises(RuntimeError, match="do not fit"):
+        f.functional.correlation_forward_cat(a, b, cat2, 1, 0.1, *prm)
+
+
+@needs_models
+@pytest.mark.parametrize("name", ["FlowNet2C", "FlowNet2"])
+def test_fused_forwards_match_unfused_models(name):
+    """flownet2_b200.fused on the unmodified reference network object vs its own forward() on the drop-in modules."""
+    from flownet2_b200 import compat, fused
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(6)
+    x = (torch.rand(2, 3, 2, 128, 192, generator=g) * 255.0).cuda()
+    net = _build_ref_model(name, "B2")
+    with torch.no_grad():
+        base = net(x)
+    fz = fused.fused_forward(net, x)
+    compat.uninstall()
+    assert fz.shape == base.shape
+    assert rel_err(fz.cpu().numpy(), base.cpu().numpy()) < 1e-4, rel_err(fz.cpu().numpy(), base.cpu().numpy())

@@ -79,12 +79,17 @@ if which in ("cn", "all"):
             xh = x.to(dev).to(dt)
             oh = F2.channelnorm_forward(xh)
             F2.channelnorm_backward(xh, oh, go.to(dev).to(dt))
-if which in ("fused", "all") and hasattr(F2, "warp_diff_norm_concat_forward"):
+if which in ("fused", "all"):
     g = torch.Generator().manual_seed(11)
     x = torch.rand(2, 6, 24, 40, generator=g)
-    flow = torch.randn(2, 2, 24, 40, generator=g) * 3
-    cat = F2.warp_diff_norm_concat_forward(x.to(dev), flow.to(dev), 20.0)
-    errs["fused_fwd"] = rel(cat, orc.warp_diff_norm_concat_forward(x.numpy(), flow.numpy(), 20.0))
+    lr = torch.randn(2, 2, 6, 10, generator=g) * 0.3
+    cat = F2.warp_concat_forward(x.to(dev), lr.to(dev), upsample="bilinear", flow_mul=20.0, flow_div=20.0)
+    errs["fused_fwd"] = rel(cat, orc.warp_concat_forward(x.numpy(), lr.numpy(), upsample_mode=1, flow_mul=20.0, flow_div=20.0))
+    a, b = rnd((1, 64, 12, 20), 12), rnd((1, 64, 12, 20), 13)
+    buf = torch.zeros(1, 32 + 441, 12, 20, device=dev)
+    F2.correlation_forward_cat(a.to(dev), b.to(dev), buf, 32, 0.1, 20, 1, 20, 1, 2)
+    ref = orc.correlation_forward(a.numpy(), b.numpy(), 20, 1, 20, 1, 2)
+    errs["corr_cat_leaky"] = rel(buf[:, 32:], np.where(ref > 0, ref, ref * np.float32(0.1)))
 torch.cuda.synchronize()
 bad = {k: v for k, v in errs.items() if not v <= 1e-4}
 print("[sanitize_ops %s] launches=%d max_err=%.2e bad=%s" % (which, F2.launch_count(), max(errs.values()) if errs else 0.0, bad), flush=True)
