@@ -450,6 +450,13 @@ def extras_ours(dev):
     rec("channelnorm_bwd_c3", lambda i: (lambda: F2.channelnorm_backward(imgs[i], o1[i], o1[(i + 1) % NS], out=o3[i])), hw * 8)
     rec("channelnorm_fwd_c2", lambda i: (lambda: F2.channelnorm_forward(flows[i], out=o1[i])), hw * 3)
     rec("channelnorm_bwd_c2", lambda i: (lambda: F2.channelnorm_backward(flows[i], o1[i], o1[(i + 1) % NS], out=o2[i])), hw * 6)
+    # 16-bit storage variants: half the bytes of the fp32 kernels
+    himgs = [t.half() for t in imgs]
+    ho1 = [torch.empty(B, 1, H, W, device=dev, dtype=torch.float16) for _ in range(NS)]
+    ho3 = [torch.empty(B, 3, H, W, device=dev, dtype=torch.float16) for _ in range(NS)]
+    rec("channelnorm_fwd_c3_fp16", lambda i: (lambda: F2.channelnorm_forward(himgs[i], out=ho1[i])), hw * 2)
+    rec("channelnorm_bwd_c3_fp16", lambda i: (lambda: F2.channelnorm_backward(himgs[i], ho1[i], ho1[(i + 1) % NS], out=ho3[i])), hw * 4)
+    del himgs, ho1, ho3
     # hot L2 (the same buffer set every launch; working sets of 117-191 MB vs 126 MB of L2: partly resident)
     rec("resample2d_fwd_hotL2", lambda i: (lambda: F2.resample2d_forward(imgs[0], flows[0], out=o3[0])), hw * 8)
     rec("resample2d_bwd_hotL2", lambda i: (lambda: F2.resample2d_backward(imgs[0], flows[0], gos[0], out1=o3[0], out2=o2[0])), hw * 13)

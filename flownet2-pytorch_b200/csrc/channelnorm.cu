@@ -111,7 +111,8 @@ channelnorm_bwd_scalar(const float *__restrict__ in, const float *__restrict__ o
 
 // ---- 16-bit storage variants (the reference dispatches K8/K9 on half too, channelnorm_kernel.cu:111,152:
 // ChannelNorm is the one custom layer that sees fp16 tensors in --fp16 mode, models.py:39).  Same
-// arithmetic as the reference: square in the storage type's value, accumulate / divide in fp32, round once.
+// arithmetic as the reference: `val * val` is a product of two scalar_t, i.e. ROUNDED to the storage type before
+// it is widened and accumulated in fp32 (channelnorm_kernel.cu:55-56); the backward divides in fp32 and rounds once.
 template <typename T> __device__ __forceinline__ float h2f(T v);
 template <> __device__ __forceinline__ float h2f<__half>(__half v) { return __half2float(v); }
 template <> __device__ __forceinline__ float h2f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
@@ -134,7 +135,7 @@ channelnorm_fwd_h8(const T *__restrict__ in, T *__restrict__ out, int C, int hw8
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float x = h2f<T>(v[i]);
-            acc[i] += x * x;
+            acc[i] += h2f<T>(f2h<T>(x * x));
         }
     }
     uint4 o;
@@ -153,7 +154,7 @@ channelnorm_fwd_h1(const T *__restrict__ in, T *__restrict__ out, int C, int hw,
     float acc = 0.f;
     for (int c = 0; c < C; ++c) {
         float x = h2f<T>(in[((long)b * C + c) * hw + p]);
-        acc += x * x;
+        acc += h2f<T>(f2h<T>(x * x));
     }
     out[idx] = f2h<T>(sqrtf(acc));
 }
@@ -169,6 +170,36 @@ channelnorm_bwd_h1(const T *__restrict__ in, const T *__restrict__ out, const T 
     for (int c = 0; c < C; ++c) {
         long i = ((long)b * C + c) * hw + p;
         gin[i] = f2h<T>(cn_bwd(g, h2f<T>(in[i]), o));
+    }
+}
+
+// one thread = 8 consecutive pixels: norm and gradOutput once (128-bit loads), then one 128-bit load + store per channel
+template <typename T>
+__global__ void __launch_bounds__(256)
+channelnorm_bwd_h8(const T *__restrict__ in, const T *__restrict__ out, const T *__restrict__ gout,
+                   T *__restrict__ gin, int C, int hw8, long n8) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n8) return;
+    int b = (int)(idx / hw8);
+    int p = (int)(idx - (long)b * hw8);
+    const uint4 oraw = *reinterpret_cast<const uint4 *>(out + idx * 8);
+    const uint4 graw = *reinterpret_cast<const uint4 *>(gout + idx * 8);
+    const T *ov = reinterpret_cast<const T *>(&oraw), *gv = reinterpret_cast<const T *>(&graw);
+    float o[8], g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        o[i] = h2f<T>(ov[i]);
+        g[i] = h2f<T>(gv[i]);
+    }
+    for (int c = 0; c < C; ++c) {
+        const long off = (((long)b * C + c) * hw8 + p) * 8;
+        const uint4 raw = *reinterpret_cast<const uint4 *>(in + off);
+        const T *v = reinterpret_cast<const T *>(&raw);
+        uint4 res;
+        T *rv = reinterpret_cast<T *>(&res);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] = f2h<T>(cn_bwd(g[i], h2f<T>(v[i]), o[i]));
+        *reinterpret_cast<uint4 *>(gin + off) = res;
     }
 }
 
@@ -189,9 +220,17 @@ template <typename T>
 static int channelnorm_backward_16(const void *in, const void *out, const void *gout, void *gin, int B, int C,
                                    int H, int W, cudaStream_t st) {
     const int hw = H * W, Tn = 256;
-    long n = (long)B * hw;
-    channelnorm_bwd_h1<T><<<(unsigned)((n + Tn - 1) / Tn), Tn, 0, st>>>((const T *)in, (const T *)out, (const T *)gout,
-                                                                        (T *)gin, C, hw, n);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) |
+                         reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(gin);
+    if (hw % 8 == 0 && (al & 15) == 0) {
+        long n8 = (long)B * (hw / 8);
+        channelnorm_bwd_h8<T><<<(unsigned)((n8 + Tn - 1) / Tn), Tn, 0, st>>>((const T *)in, (const T *)out, (const T *)gout,
+                                                                             (T *)gin, C, hw / 8, n8);
+    } else {
+        long n = (long)B * hw;
+        channelnorm_bwd_h1<T><<<(unsigned)((n + Tn - 1) / Tn), Tn, 0, st>>>((const T *)in, (const T *)out, (const T *)gout,
+                                                                            (T *)gin, C, hw, n);
+    }
     count_launch();
     return check_launch("channelnorm_backward(16-bit)");
 }

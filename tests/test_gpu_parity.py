@@ -587,6 +587,31 @@ def test_resample_channelnorm_vs_reference_kernels():
     assert_close(f.functional.channelnorm_backward(x, o, gon).cpu().numpy(), rgi.cpu().numpy(), 1e-5, "cnorm bwd vs ref")
 
 
+@needs_ref
+@pytest.mark.parametrize("shape", [(2, 3, 16, 24), (1, 2, 7, 9), (2, 3, 64, 128)])
+def test_channelnorm_half_vs_reference_half_kernels(shape):
+    """our fp16 ChannelNorm kernels (8 pixels per thread, fwd and bwd; scalar kernels for ragged sizes)
+    against the reference's OWN half dispatch (channelnorm_kernel.cu:111,152) through oracle/_ref.  The forward
+    reproduces the reference's arithmetic exactly (squares rounded to half, fp32 accumulation): bit-identical.  The
+    backward's divide is fp32 here and double there before the single rounding to half: at most 1 half ulp apart."""
+    f = _f2()
+    cn = oref.load_extension("channelnorm_cuda")
+    x = _randn(shape, 35).cuda().half()
+    ro = torch.zeros(shape[0], 1, shape[2], shape[3], device="cuda", dtype=torch.float16)
+    cn.forward(x, ro, 2)
+    o = f.functional.channelnorm_forward(x)
+    assert o.dtype == torch.float16 and torch.equal(o, ro)
+    go = _randn(tuple(ro.shape), 36).cuda().half()
+    rgi = torch.zeros_like(x)
+    cn.backward(x, ro, go, rgi, 2)
+    gi = f.functional.channelnorm_backward(x, o, go)
+    assert gi.dtype == torch.float16
+    d = (gi.float() - rgi.float()).abs()
+    ulp = torch.maximum(rgi.float().abs(), torch.tensor(6.1e-5, device="cuda")) * 2.0 ** -10
+    assert bool((d <= ulp).all()), float((d / ulp).max())
+    assert float((d > 0).float().mean()) < 0.01
+
+
 needs_models = pytest.mark.skipif(not (oref.available() and oref.python_tree_available()),
                                   reason="reference python tree / extensions not installed under baseline/_ref, oracle/_ref")
 
