@@ -205,6 +205,25 @@ int fn2b200_correlation_backward_ws(const float *in1, const float *in2, const fl
                                         corr_type_multiply, stream);
 }
 
+// shared argument checks of the fused warp-concat entry points
+static int check_warp_layout(const char *who, int C, int cat_channels, int ch_x, int n_x, int ch_warped, int ch_flow,
+                             float flow_div, int ch_flow_norm, int ch_diff_norm) {
+    struct { int ch, n; const char *what; } slots[5] = {{ch_x, n_x, "x"}, {ch_warped, C, "warped"}, {ch_flow, 2, "flow"},
+                                                         {ch_flow_norm, 1, "flow norm"}, {ch_diff_norm, 1, "diff norm"}};
+    for (int i = 0; i < 5; ++i) {
+        if (slots[i].ch < 0) continue;
+        if (slots[i].n < 0 || slots[i].ch + slots[i].n > cat_channels)
+            return fail(FN2B200_EINVAL, "%s: %s channels [%d, %d) outside the %d-channel output", who, slots[i].what,
+                        slots[i].ch, slots[i].ch + slots[i].n, cat_channels);
+        for (int j = 0; j < i; ++j)
+            if (slots[j].ch >= 0 && slots[i].ch < slots[j].ch + slots[j].n && slots[j].ch < slots[i].ch + slots[i].n)
+                return fail(FN2B200_EINVAL, "%s: %s and %s channel ranges overlap", who, slots[i].what, slots[j].what);
+    }
+    if (ch_x >= 0 && n_x > 2 * C) return fail(FN2B200_EINVAL, "%s: n_x=%d > 2C", who, n_x);
+    if (ch_flow >= 0 && flow_div == 0.f) return fail(FN2B200_EINVAL, "%s: flow_div = 0", who);
+    return 0;
+}
+
 static int check_resample(const char *who, const int64_t *istride, int B, int C, int iH, int iW,
                           int H, int W, int kernel_size) {
     if (B < 0 || C <= 0 || iH <= 0 || iW <= 0 || H <= 0 || W <= 0)
@@ -271,19 +290,8 @@ int fn2b200_warp_concat_forward(const float *x, const int64_t *xstride, int C, c
     if (!xstride) return fail(FN2B200_ENULL, "warp_concat_forward: null stride array");
     int rc = check_flow_src("warp_concat_forward", flow, fh, fw, upsample_mode, H, W);
     if (rc) return rc;
-    struct { int ch, n; const char *what; } slots[5] = {{ch_x, n_x, "x"}, {ch_warped, C, "warped"}, {ch_flow, 2, "flow"},
-                                                         {ch_flow_norm, 1, "flow norm"}, {ch_diff_norm, 1, "diff norm"}};
-    for (int i = 0; i < 5; ++i) {
-        if (slots[i].ch < 0) continue;
-        if (slots[i].n < 0 || slots[i].ch + slots[i].n > cat_channels)
-            return fail(FN2B200_EINVAL, "warp_concat_forward: %s channels [%d, %d) outside the %d-channel output",
-                        slots[i].what, slots[i].ch, slots[i].ch + slots[i].n, cat_channels);
-        for (int j = 0; j < i; ++j)
-            if (slots[j].ch >= 0 && slots[i].ch < slots[j].ch + slots[j].n && slots[j].ch < slots[i].ch + slots[i].n)
-                return fail(FN2B200_EINVAL, "warp_concat_forward: %s and %s channel ranges overlap", slots[i].what, slots[j].what);
-    }
-    if (ch_x >= 0 && n_x > 2 * C) return fail(FN2B200_EINVAL, "warp_concat_forward: n_x=%d > 2C", n_x);
-    if (ch_flow >= 0 && flow_div == 0.f) return fail(FN2B200_EINVAL, "warp_concat_forward: flow_div = 0");
+    if ((rc = check_warp_layout("warp_concat_forward", C, cat_channels, ch_x, n_x, ch_warped, ch_flow, flow_div, ch_flow_norm,
+                                ch_diff_norm))) return rc;
     if ((int64_t)B * cat_channels * H * W >= (1LL << 31)) return fail(FN2B200_EINVAL, "warp_concat_forward: tensor exceeds 2^31 elements");
     if (B == 0) return 0;
     if (!x || !cat) return fail(FN2B200_ENULL, "warp_concat_forward: null pointer");
@@ -305,6 +313,32 @@ int fn2b200_resample2d_backward(const float *img, const int64_t *istride, const 
                                 int zero_grad_input1, void *stream) {
     return fn2b200_resample2d_backward_ws(img, istride, flow, gout, gimg, gflow, B, C, iH, iW, H, W, kernel_size, bilinear,
                                           zero_grad_input1, nullptr, 0, stream);
+}
+
+size_t fn2b200_warp_concat_backward_workspace(int B, int C, int H, int W) {
+    if (B <= 0 || C < 1 || C > 3 || H <= 0 || W <= 0) return 0;
+    return resample2d_backward_workspace_bytes(B, H, W);
+}
+
+int fn2b200_warp_concat_backward(const float *x, const int64_t *xstride, int C, const float *flow, const float *grad_cat,
+                                 int cat_channels, int ch_x, int n_x, int ch_warped, int ch_flow, float flow_div,
+                                 int ch_flow_norm, int ch_diff_norm, float *grad_x, float *grad_flow, void *workspace,
+                                 size_t workspace_bytes, int B, int H, int W, void *stream) {
+    if (B < 0 || C < 1 || H <= 0 || W <= 0 || cat_channels < 1)
+        return fail(FN2B200_EINVAL, "warp_concat_backward: bad shape B=%d C=%d H=%d W=%d cat_channels=%d", B, C, H, W, cat_channels);
+    if (C > 3) return fail(FN2B200_EUNSUPPORTED, "warp_concat_backward: C=%d > 3 (the interleaved gradient scratch holds 4 floats per pixel)", C);
+    if (!xstride) return fail(FN2B200_ENULL, "warp_concat_backward: null stride array");
+    int rc = check_warp_layout("warp_concat_backward", C, cat_channels, ch_x, n_x, ch_warped, ch_flow, flow_div, ch_flow_norm,
+                               ch_diff_norm);
+    if (rc) return rc;
+    if ((int64_t)B * cat_channels * H * W >= (1LL << 31)) return fail(FN2B200_EINVAL, "warp_concat_backward: tensor exceeds 2^31 elements");
+    if (B == 0) return 0;
+    if (!x || !flow || !grad_cat || !grad_x || !grad_flow) return fail(FN2B200_ENULL, "warp_concat_backward: null pointer");
+    if (!workspace || workspace_bytes < resample2d_backward_workspace_bytes(B, H, W) || (reinterpret_cast<uintptr_t>(workspace) & 15))
+        return fail(FN2B200_EINVAL, "warp_concat_backward: needs a 16-byte aligned workspace of fn2b200_warp_concat_backward_workspace() bytes");
+    if ((rc = bind_device_of(flow))) return rc;
+    WarpOut o = {nullptr, cat_channels, ch_x, n_x, ch_warped, ch_flow, ch_flow_norm, ch_diff_norm, flow_div};
+    return warp_concat_backward_tile(x, xstride, flow, grad_cat, o, grad_x, grad_flow, workspace, B, C, H, W, (cudaStream_t)stream);
 }
 
 size_t fn2b200_resample2d_backward_workspace(const int64_t *istride, int B, int C, int iH, int iW, int H, int W) {

@@ -164,7 +164,11 @@ int resample2d_backward_tile(const float *img, const int64_t *istride, const flo
                              float *gflow, void *workspace, int scatter, int accumulate, int B, int C, int iH, int iW,
                              int H, int W, cudaStream_t st);
 size_t resample2d_backward_workspace_bytes(int B, int iH, int iW);
-int resample2d_backward_finish(const float *T, float *gimg, int accumulate, int B, int C, int iH, int iW, cudaStream_t st);
+int resample2d_backward_finish(const float *T, float *gimg, int accumulate, int B, int C, int iH, int iW, cudaStream_t st,
+                               long gimg_bstride = 0);
+// backward of the fused warp -> diff -> channel-norm -> concat forward (full-resolution flow, C <= 3); workspace as above
+int warp_concat_backward_tile(const float *x, const int64_t *xstride, const float *flow, const float *gcat, const WarpOut &o,
+                              float *gx, float *gflow, void *workspace, int B, int C, int H, int W, cudaStream_t st);
 
 struct CorrParams {
     int B, C, H, W;        // inputs [B,C,H,W]

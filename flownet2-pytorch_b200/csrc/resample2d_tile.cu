@@ -215,15 +215,111 @@ resample2d_bwd_tile(ImgView im, FlowSrc fs, const float *__restrict__ gout, floa
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of the fused warp -> diff -> channel-norm -> concat forward (full-resolution flow; in a training graph the
+// x4 upsample stays a torch module in front of it).  Per pixel, with v = the warped img1 (recomputed from the taps the
+// flow gradient needs anyway), d = img0 - v, n = |d|, f = |flow|:
+//   g_d[c]   = gcat[ch_dnorm] * d[c] / (n + 1e-9)                      ChannelNorm backward, channelnorm_kernel.cu:92
+//   g_v[c]   = gcat[ch_warped + c] - g_d[c]                            the subtraction (models.py:134)
+//   gx[c]    = gcat[ch_x + c] + g_d[c]          (img0 half),   gx[C + c] = gcat[ch_x + C + c] + scatter of g_v (K6)
+//   gflow    = K7(g_v) + gcat[ch_flow ..] / flow_div + gcat[ch_fnorm] * flow / (f + 1e-9)
+// The scatter goes through the interleaved scratch T exactly as in resample2d_bwd_tile<.., 2>; the finishing kernel adds
+// T to the direct term this kernel stores into gx[:, C:2C].
+// ---------------------------------------------------------------------------------------------------------------
+template <int CT, int PY>
+__global__ void __launch_bounds__(256)
+warp_concat_bwd_tile(ImgView xv, FlowSrc fs, const float *__restrict__ gcat, WarpOut o, float *__restrict__ gx,
+                     float *__restrict__ T, float *__restrict__ gflow, int H, int W, int tiles_x, int tiles_y) {
+    const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+    int t = blockIdx.x;
+    const int bxi = t % tiles_x;
+    t /= tiles_x;
+    const int byi = t % tiles_y, b = t / tiles_y;
+    const int x = bxi * 32 + lx, y0 = byi * (8 * PY) + ly;
+    if (x >= W) return;
+    const long hw = (long)H * W;
+    const float *i0 = xv.p + (long)b * xv.sb, *i1 = i0 + CT * xv.sc;
+    const float *gc = gcat + (long)b * o.cat_channels * hw;
+    float *gxb = gx + (long)b * 2 * CT * hw;
+    float *Tb = T + (long)b * hw * 4;
+#pragma unroll
+    for (int j = 0; j < PY; ++j) {
+        const int y = y0 + 8 * j;
+        if (y >= H) continue;
+        const long pix = (long)y * W + x;
+        const float2 fl = load_flow(fs, b, y, x, H, W);
+        const float xf = (float)x + fl.x, yf = (float)y + fl.y;
+        const float fx = floorf(xf), fy = floorf(yf);
+        const float al = xf - fx, be = yf - fy;
+        const Taps tp = clamp_taps(fx, fy, W, H);
+        const float w00 = (1.f - al) * (1.f - be), w01 = al * (1.f - be), w10 = (1.f - al) * be, w11 = al * be;
+        const long oTL = tp.yT * xv.sh + tp.xL * xv.sw, oTR = tp.yT * xv.sh + tp.xR * xv.sw;
+        const long oBL = tp.yB * xv.sh + tp.xL * xv.sw, oBR = tp.yB * xv.sh + tp.xR * xv.sw;
+        float iTL[CT], iTR[CT], iBL[CT], iBR[CT], d[CT];
+        float nacc = 0.f;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float *ic = i1 + c * xv.sc;
+            iTL[c] = __ldg(ic + oTL); iTR[c] = __ldg(ic + oTR); iBL[c] = __ldg(ic + oBL); iBR[c] = __ldg(ic + oBR);
+            float v = __fmul_rn(w00, iTL[c]);
+            v = __fmaf_rn(w01, iTR[c], v);
+            v = __fmaf_rn(w10, iBL[c], v);
+            v = __fmaf_rn(w11, iBR[c], v);
+            d[c] = __ldg(i0 + c * xv.sc + (long)y * xv.sh + x * xv.sw) - v;
+            nacc = __fmaf_rn(d[c], d[c], nacc);
+        }
+        const float nrm = sqrtf(nacc);
+        const float gn = o.ch_dnorm >= 0 ? ldg_stream1(gc + (long)o.ch_dnorm * hw + pix) : 0.f;
+        float gv[3] = {0.f, 0.f, 0.f};
+        float gfx = 0.f, gfy = 0.f;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float gd = o.ch_dnorm >= 0 ? gn * d[c] / (nrm + 1e-9f) : 0.f;
+            const float gw = o.ch_warped >= 0 ? ldg_stream1(gc + (long)(o.ch_warped + c) * hw + pix) : 0.f;
+            gv[c] = gw - gd;
+            const float gx0 = (o.ch_x >= 0 && c < o.n_x) ? ldg_stream1(gc + (long)(o.ch_x + c) * hw + pix) : 0.f;
+            const float gx1 = (o.ch_x >= 0 && CT + c < o.n_x) ? ldg_stream1(gc + (long)(o.ch_x + CT + c) * hw + pix) : 0.f;
+            __stcs(gxb + (long)c * hw + pix, gx0 + gd);
+            __stcs(gxb + (long)(CT + c) * hw + pix, gx1);          // + the scattered part, added by the finishing kernel
+            // K7: d/dxf with gamma = 1 - beta (:181-192), d/dyf with gamma = 1 - alpha (:168-179)
+            gfx += gv[c] * ((1.f - be) * (iTR[c] - iTL[c]) + be * (iBR[c] - iBL[c]));
+            gfy += gv[c] * ((1.f - al) * (iBL[c] - iTL[c]) + al * (iBR[c] - iTR[c]));
+        }
+        // K6: image-gradient scatter, int()-truncation fractions (:105-114); image dims == flow dims here
+        const float at = xf - (float)(int)xf, bt = yf - (float)(int)yf;
+        const float s00 = (1.f - at) * (1.f - bt), s01 = at * (1.f - bt), s10 = (1.f - at) * bt, s11 = at * bt;
+        float *pTL = Tb + ((long)tp.yT * W + tp.xL) * 4, *pTR = Tb + ((long)tp.yT * W + tp.xR) * 4;
+        float *pBL = Tb + ((long)tp.yB * W + tp.xL) * 4, *pBR = Tb + ((long)tp.yB * W + tp.xR) * 4;
+        red_add_v4(pTL, s00 * gv[0], s00 * gv[1], s00 * gv[2], 0.f);
+        red_add_v4(pTR, s01 * gv[0], s01 * gv[1], s01 * gv[2], 0.f);
+        red_add_v4(pBL, s10 * gv[0], s10 * gv[1], s10 * gv[2], 0.f);
+        red_add_v4(pBR, s11 * gv[0], s11 * gv[1], s11 * gv[2], 0.f);
+        if (o.ch_flow >= 0) {
+            gfx += ldg_stream1(gc + (long)o.ch_flow * hw + pix) / o.flow_div;
+            gfy += ldg_stream1(gc + (long)(o.ch_flow + 1) * hw + pix) / o.flow_div;
+        }
+        if (o.ch_fnorm >= 0) {
+            const float fnrm = sqrtf(__fmaf_rn(fl.y, fl.y, __fmul_rn(fl.x, fl.x)));
+            const float gf = ldg_stream1(gc + (long)o.ch_fnorm * hw + pix);
+            gfx += gf * fl.x / (fnrm + 1e-9f);
+            gfy += gf * fl.y / (fnrm + 1e-9f);
+        }
+        float *gfp = gflow + (long)b * 2 * hw + pix;
+        __stcs(gfp, gfx);
+        __stcs(gfp + hw, gfy);
+    }
+}
+
 // T[b][y][x][4] -> gimg[b][c][y][x] (accumulate != 0: added to what gimg holds -- the *_cuda shim's caller-zeroed buffer)
 template <int CT>
 __global__ void __launch_bounds__(256)
-resample2d_bwd_finish(const float *__restrict__ T, float *__restrict__ gimg, long hw, long npix, int accumulate) {
+resample2d_bwd_finish(const float *__restrict__ T, float *__restrict__ gimg, long hw, long npix, long gimg_bstride,
+                      int accumulate) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= npix) return;
     const long b = idx / hw, p = idx - b * hw;
     const float4 t = ldg_stream4(T + idx * 4);
-    float *o = gimg + b * CT * hw + p;
+    float *o = gimg + b * gimg_bstride + p;
     const float v[3] = {t.x, t.y, t.z};
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
@@ -324,16 +420,40 @@ int resample2d_backward_tile(const float *img, const int64_t *is, const float *f
     return resample2d_backward_finish(T, gimg, accumulate, B, C, iH, iW, st);
 }
 
-int resample2d_backward_finish(const float *T, float *gimg, int accumulate, int B, int C, int iH, int iW, cudaStream_t st) {
+int resample2d_backward_finish(const float *T, float *gimg, int accumulate, int B, int C, int iH, int iW, cudaStream_t st,
+                               long gimg_bstride) {
     const long ihw = (long)iH * iW, npix = (long)B * ihw;
+    const long bs = gimg_bstride ? gimg_bstride : (long)C * ihw;
     const unsigned g2 = (unsigned)((npix + 255) / 256);
     switch (C) {
-        case 1: resample2d_bwd_finish<1><<<g2, 256, 0, st>>>(T, gimg, ihw, npix, accumulate); break;
-        case 2: resample2d_bwd_finish<2><<<g2, 256, 0, st>>>(T, gimg, ihw, npix, accumulate); break;
-        default: resample2d_bwd_finish<3><<<g2, 256, 0, st>>>(T, gimg, ihw, npix, accumulate); break;
+        case 1: resample2d_bwd_finish<1><<<g2, 256, 0, st>>>(T, gimg, ihw, npix, bs, accumulate); break;
+        case 2: resample2d_bwd_finish<2><<<g2, 256, 0, st>>>(T, gimg, ihw, npix, bs, accumulate); break;
+        default: resample2d_bwd_finish<3><<<g2, 256, 0, st>>>(T, gimg, ihw, npix, bs, accumulate); break;
     }
     count_launch();
     return check_launch("resample2d_backward (finish)");
+}
+
+int warp_concat_backward_tile(const float *x, const int64_t *xs, const float *flow, const float *gcat, const WarpOut &o,
+                              float *gx, float *gflow, void *workspace, int B, int C, int H, int W, cudaStream_t st) {
+    const int tiles_x = (W + 31) / 32, tiles_y = (H + 15) / 16;          // PY = 2: 16 live tap registers per channel set
+    const long ntiles = (long)tiles_x * tiles_y * B;
+    if (ntiles >= (1L << 31)) return fail(FN2B200_EINVAL, "warp_concat_backward: %ld tiles exceed the grid limit", ntiles);
+    float *T = static_cast<float *>(workspace);
+    cudaError_t e = cudaMemsetAsync(T, 0, resample2d_backward_workspace_bytes(B, H, W), st);
+    if (e != cudaSuccess) return fail((int)e, "warp_concat_backward: workspace memset failed (%s)", cudaGetErrorString(e));
+    const ImgView v = view_of(x, xs);
+    const FlowSrc fs = {flow, H, W, 0, 1.f};
+    const unsigned grid = (unsigned)ntiles;
+    switch (C) {
+        case 1: warp_concat_bwd_tile<1, 2><<<grid, 256, 0, st>>>(v, fs, gcat, o, gx, T, gflow, H, W, tiles_x, tiles_y); break;
+        case 2: warp_concat_bwd_tile<2, 2><<<grid, 256, 0, st>>>(v, fs, gcat, o, gx, T, gflow, H, W, tiles_x, tiles_y); break;
+        default: warp_concat_bwd_tile<3, 2><<<grid, 256, 0, st>>>(v, fs, gcat, o, gx, T, gflow, H, W, tiles_x, tiles_y); break;
+    }
+    count_launch();
+    if (int rc = check_launch("warp_concat_backward")) return rc;
+    // gx[:, C:2C] += T
+    return resample2d_backward_finish(T, gx + (long)C * H * W, 1, B, C, H, W, st, (long)2 * C * H * W);
 }
 
 }  // namespace fn2

@@ -12,12 +12,48 @@ and hyper-parameters are used as they are) and run the same data flow with the g
   ONE kernel (``functional.warp_concat_forward``, 8f-1) that reads the quarter-resolution flow directly (8f-3) and writes
   the concat buffer the next sub-network consumes.
 
-Inference only (``torch.no_grad`` is entered here): training keeps the differentiable drop-in modules.  Results
+The model-level forwards are inference only (``torch.no_grad`` is entered there); for training graphs there is
+``WarpConcat`` / ``WarpConcatFunction`` (full-resolution flow, fused forward AND fused backward) next to the
+differentiable drop-in modules.  Results
 agree with the unfused graph to rounding (tests/test_gpu_parity.py::test_fused_forwards_match_unfused_models).
 """
 import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from . import functional as F2
+
+
+class WarpConcatFunction(Function):
+    """concat1 = cat(x, Resample2d()(x[:, 3:], flow), flow / div_flow, ChannelNorm()(x[:, :3] - warped)) as one
+    differentiable op (models.py:133-138, :145-150); flow is the full-resolution flow (keep nn.Upsample in front of it
+    when training: its backward is torch's).  forward and backward are one kernel each."""
+
+    @staticmethod
+    def forward(ctx, x, flow, div_flow=20.0):
+        ctx.save_for_backward(x, flow)
+        ctx.div_flow = float(div_flow)
+        return F2.warp_concat_forward(x, flow, C=x.size(1) // 2, flow_div=ctx.div_flow)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_cat):
+        x, flow = ctx.saved_tensors
+        gx, gf = F2.warp_concat_backward(x, flow, grad_cat, C=x.size(1) // 2, flow_div=ctx.div_flow)
+        if x.size(1) > gx.size(1):           # odd trailing channels of x take no part
+            gx = torch.cat((gx, gx.new_zeros(gx.size(0), x.size(1) - gx.size(1), gx.size(2), gx.size(3))), 1)
+        return (gx if ctx.needs_input_grad[0] else None), (gf if ctx.needs_input_grad[1] else None), None
+
+
+class WarpConcat(torch.nn.Module):
+    """nn.Module form of WarpConcatFunction: WarpConcat(div_flow)(x, flow) -> the (3C + 3)-channel concat."""
+
+    def __init__(self, div_flow=20.0):
+        super(WarpConcat, self).__init__()
+        self.div_flow = div_flow
+
+    def forward(self, x, flow):
+        return WarpConcatFunction.apply(x, flow, self.div_flow)
 
 
 def _corr_module(net_c):

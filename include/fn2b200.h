@@ -192,6 +192,20 @@ int fn2b200_warp_concat_forward(const float *x, const int64_t *xstride, int C, c
                                 int ch_warped, int ch_flow, float flow_div, int ch_flow_norm, int ch_diff_norm, int B,
                                 int H, int W, void *stream);
 
+/*
+ * Backward of fn2b200_warp_concat_forward for a full-resolution flow (upsample_mode 0; in a training graph the x4
+ * upsample stays a module in front of it), C <= 3.  grad_cat: [B, cat_channels, H, W]; the ch_* layout must be the
+ * forward's.  grad_x: [B, 2C, H, W] and grad_flow: [B, 2, H, W], contiguous, fully overwritten.  The composition of
+ * the reference modules' own backward passes (torch.cat, the division, ChannelNorm with its 1e-9, the subtraction,
+ * Resample2d's K6 scatter and K7 flow gradient) in one kernel plus the transpose of the scatter scratch.
+ * workspace: fn2b200_warp_concat_backward_workspace(B, C, H, W) bytes, 16-byte aligned.
+ */
+size_t fn2b200_warp_concat_backward_workspace(int B, int C, int H, int W);
+int fn2b200_warp_concat_backward(const float *x, const int64_t *xstride, int C, const float *flow, const float *grad_cat,
+                                 int cat_channels, int ch_x, int n_x, int ch_warped, int ch_flow, float flow_div,
+                                 int ch_flow_norm, int ch_diff_norm, float *grad_x, float *grad_flow, void *workspace,
+                                 size_t workspace_bytes, int B, int H, int W, void *stream);
+
 /* input1: [B,C,H,W]; output: [B,1,H,W] = sqrt(sum_c x^2).  norm_deg is ignored (reference: same). */
 int fn2b200_channelnorm_forward(const float *input1, float *output, int B, int C, int H, int W,
                                 int norm_deg, void *stream);

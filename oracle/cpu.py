@@ -207,3 +207,37 @@ def warp_concat_forward(x, flow, C=3, upsample_mode=0, flow_mul=1.0, cat_channel
     if ch_diff_norm >= 0:
         cat[:, ch_diff_norm:ch_diff_norm + 1] = channelnorm_forward(x[:, :C] - warped)
     return cat
+
+
+def warp_concat_backward(x, flow, grad_cat, C=3, flow_div=1.0, ch_x=0, n_x=None, ch_warped=None, ch_flow=None, ch_flow_norm=-1,
+                         ch_diff_norm=None):
+    """Backward of warp_concat_forward(upsample_mode=0) as the composition of the reference modules' own backward passes:
+    torch.cat (slicing), the division, ChannelNorm (channelnorm_kernel.cu:63-96), the subtraction, Resample2d
+    (resample2d_kernel.cu:75-198).  Returns (grad_x [B,2C,H,W], grad_flow [B,2,H,W])."""
+    x = np.ascontiguousarray(x, np.float32)
+    flow = np.ascontiguousarray(flow, np.float32)
+    g = np.ascontiguousarray(grad_cat, np.float32)
+    n_x = 2 * C if n_x is None else n_x
+    ch_warped = 2 * C if ch_warped is None else ch_warped
+    ch_flow = 3 * C if ch_flow is None else ch_flow
+    ch_diff_norm = 3 * C + 2 if ch_diff_norm is None else ch_diff_norm
+    img0, img1 = x[:, :C], np.ascontiguousarray(x[:, C:2 * C])
+    warped = resample2d_forward(img1, flow)
+    diff = img0 - warped
+    g_diff = np.zeros_like(diff)
+    if ch_diff_norm >= 0:
+        g_diff = channelnorm_backward(diff, channelnorm_forward(diff), g[:, ch_diff_norm:ch_diff_norm + 1])
+    g_warped = -g_diff
+    if ch_warped >= 0:
+        g_warped = g_warped + g[:, ch_warped:ch_warped + C]
+    g_img1, g_flow = resample2d_backward(img1, flow, g_warped)
+    gx = np.zeros((x.shape[0], 2 * C) + x.shape[2:], np.float32)
+    gx[:, :C] = g_diff
+    gx[:, C:] = g_img1
+    if ch_x >= 0:
+        gx[:, :n_x] += g[:, ch_x:ch_x + n_x]
+    if ch_flow >= 0:
+        g_flow = g_flow + g[:, ch_flow:ch_flow + 2] / np.float32(flow_div)
+    if ch_flow_norm >= 0:
+        g_flow = g_flow + channelnorm_backward(flow, channelnorm_forward(flow), g[:, ch_flow_norm:ch_flow_norm + 1])
+    return gx, g_flow.astype(np.float32)

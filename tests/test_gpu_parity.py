@@ -380,6 +380,37 @@ def test_warp_concat_forward_vs_oracle_composition():
         f.functional.warp_concat_forward(x.cuda(), flow.cuda(), ch_warped=4)
 
 
+def test_warp_concat_backward_vs_oracle_and_unfused_autograd():
+    """The fused backward (one kernel + the scratch transpose) against the oracle's composition of the reference
+    modules' backward passes, and against torch autograd through the unfused chain of our drop-in modules."""
+    from flownet2_b200 import fused
+    f = _f2()
+    g = torch.Generator().manual_seed(27)
+    x0 = torch.rand(2, 6, 40, 72, generator=g) - 0.5
+    fl0 = torch.randn(2, 2, 40, 72, generator=g) * 4
+    gc = torch.randn(2, 12, 40, 72, generator=g)
+    x, fl = x0.cuda().requires_grad_(), fl0.cuda().requires_grad_()
+    cat = fused.WarpConcat(20.0)(x, fl)
+    cat.backward(gc.cuda())
+    rx, rf = orc.warp_concat_backward(x0.numpy(), fl0.numpy(), gc.numpy(), flow_div=20.0)
+    assert_close(x.grad.cpu().numpy(), rx, TOL, "warp_concat grad_x")
+    assert_close(fl.grad.cpu().numpy(), rf, TOL, "warp_concat grad_flow")
+    x2, fl2 = x0.cuda().requires_grad_(), fl0.cuda().requires_grad_()
+    warped = f.Resample2d()(x2[:, 3:], fl2)
+    chain = torch.cat((x2, warped, fl2 / 20.0, f.ChannelNorm()(x2[:, :3] - warped)), dim=1)
+    assert rel_err(cat.detach().cpu().numpy(), chain.detach().cpu().numpy()) < 1e-6
+    chain.backward(gc.cuda())
+    assert_close(x.grad.cpu().numpy(), x2.grad.cpu().numpy(), 1e-5, "fused vs unfused autograd grad_x")
+    assert_close(fl.grad.cpu().numpy(), fl2.grad.cpu().numpy(), 1e-5, "fused vs unfused autograd grad_flow")
+    # fusion-stage layout with a flow-norm channel, functional API
+    gc11 = torch.randn(2, 11, 40, 72, generator=g)
+    kw = dict(flow_div=1.0, ch_x=0, n_x=3, ch_warped=-1, ch_flow=3, ch_flow_norm=7, ch_diff_norm=9)
+    gx, gf = f.functional.warp_concat_backward(x0.cuda(), fl0.cuda(), gc11.cuda(), **kw)
+    rx, rf = orc.warp_concat_backward(x0.numpy(), fl0.numpy(), gc11.numpy(), **kw)
+    assert_close(gx.cpu().numpy(), rx, TOL, "warp_concat grad_x (fusion layout)")
+    assert_close(gf.cpu().numpy(), rf, TOL, "warp_concat grad_flow (fusion layout)")
+
+
 def test_resample2d_strided_image_slice_and_module():
     """FlowNet2 passes x[:,3:,:,:] (non-contiguous, models.py:133); no .contiguous() copy needed."""
     f = _f2()
