@@ -7,6 +7,9 @@ has to be visible under those names before ``import models``:
 * level B1 (strict): extension-module shims ``correlation_cuda`` / ``resample2d_cuda`` /
   ``channelnorm_cuda`` with the reference's out-parameter signatures; the reference's own Python
   wrappers (and their zero-fills / ``.contiguous()`` copy) keep running unchanged.
+* level B1p (strict, compiled): the same three names as REAL pybind extension modules
+  (``flownet2-pytorch_b200/pybind/*.cc``: ATen glue over the C ABI, built by ``pybind/build_pybind.py``) -- what the
+  reference's ``setup.py`` would produce if its ``.cc`` files called libfn2b200.
 * level B2 (fast): our ``Correlation`` / ``Resample2d`` / ``ChannelNorm`` modules are seeded as
   ``networks.*_package.*`` so models.py picks up the classes directly.
 """
@@ -27,6 +30,23 @@ def install_extension_shims():
         sys.modules[name] = importlib.import_module("flownet2_b200.shims." + name)
 
 
+def install_pybind_extensions():
+    """B1p: the compiled pybind modules (built in-tree; ImportError if they are missing -- no fallback to the Python shims)."""
+    import importlib.util
+    import os
+    import sysconfig
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pybind")
+    suffix = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
+    for name in _EXT:
+        path = os.path.join(here, name + suffix)
+        if not os.path.isfile(path):
+            raise ImportError("%s not built: run python flownet2-pytorch_b200/pybind/build_pybind.py" % path)
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        sys.modules[name] = mod
+
+
 def install_layer_modules():
     """B2: make ``from networks.correlation_package.correlation import Correlation`` etc. bind ours."""
     for ref_name, ours in _B2.items():
@@ -34,6 +54,9 @@ def install_layer_modules():
 
 
 def install(level="B2"):
+    if level == "B1p":
+        install_pybind_extensions()
+        return
     install_extension_shims()
     if level == "B2":
         install_layer_modules()

@@ -115,3 +115,28 @@ def test_api_surface_matches_reference():
             "stride1", "stride2", "corr_type_multiply"]
     finally:
         compat.uninstall()
+
+
+def test_pybind_extension_modules_build_and_export_the_reference_interface():
+    """north_star: 'a thin C++/pybind extension'.  The three modules the reference imports by name are compiled in-tree
+    (g++, no device code), export forward / backward like the reference's PYBIND11_MODULE blocks
+    (correlation_cuda.cc:169-172, resample2d_cuda.cc:28-31, channelnorm_cuda.cc:27-30) and refuse CPU tensors."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bp", os.path.join(ROOT, "flownet2-pytorch_b200", "pybind", "build_pybind.py"))
+    bp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bp)
+    for so in bp.build():
+        assert os.path.isfile(so)
+    from flownet2_b200 import compat
+    import sys
+    compat.uninstall()
+    compat.install("B1p")
+    try:
+        for name in ("correlation_cuda", "resample2d_cuda", "channelnorm_cuda"):
+            mod = sys.modules[name]
+            assert mod.__file__.endswith(".so") and callable(mod.forward) and callable(mod.backward)
+        a = torch.zeros(1, 4, 8, 8)
+        with pytest.raises(RuntimeError):        # "input1 must be a CUDA tensor" (on a box without a driver c10 may
+            sys.modules["correlation_cuda"].forward(a, a, a.new(), a.new(), a.new(), 4, 1, 4, 1, 2, 1)   # replace the text)
+    finally:
+        compat.uninstall()
