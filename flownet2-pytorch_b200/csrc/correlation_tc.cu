@@ -62,8 +62,9 @@ corr_tc_split_kernel(const float *__restrict__ in0, const float *__restrict__ in
     const float *__restrict__ in = which ? in1 : in0;
     __nv_bfloat16 *__restrict__ hi = which ? hi1 : hi0;
     __nv_bfloat16 *__restrict__ lo = which ? lo1 : lo0;
-    const int x0 = blockIdx.x * 64;
-    const int n = blockIdx.z / H, y = blockIdx.z % H;
+    // grid: x = (sample, row) -- the only dimension that may exceed 65535 --, y = (input, channel block), z = 64-px column block
+    const int x0 = blockIdx.z * 64;
+    const int n = blockIdx.x / H, y = blockIdx.x % H;
     const int Hc = H >> 1, Wc = W >> 1;
     {
         const int xo = tid & 63, cs = tid >> 6;
@@ -699,7 +700,8 @@ static int tc_env_int(const char *name, int def, int lo, int hi) {
 
 bool corr_tc_supported(const CorrParams &p) {
     return p.k == 1 && p.s1 == 1 && p.s2 == 2 && p.dr == TC_DR && p.pad == p.md && (p.H % 2 == 0) &&
-           (p.W % 2 == 0) && (p.C % TC_KB == 0) && p.C <= TC_KB * TC_MAXKB && p.H >= 2 && p.W >= 2;
+           (p.W % 2 == 0) && (p.C % TC_KB == 0) && p.C <= TC_KB * TC_MAXKB && p.H >= 2 && p.W >= 2 &&
+           (p.W + 63) / 64 <= 65535;          // the split pass's grid z extent (x carries B * H)
 }
 
 size_t corr_tc_workspace_bytes(const CorrParams &p) {
@@ -709,7 +711,7 @@ size_t corr_tc_workspace_bytes(const CorrParams &p) {
 // workspace layout: [hi(in1) | lo(in1) | hi(in2) | lo(in2)], each B*C*H*W bf16
 static int corr_tc_split(const float *in1, const float *in2, __nv_bfloat16 *w, const CorrParams &p, cudaStream_t st) {
     const size_t per = (size_t)p.B * p.C * p.H * p.W;
-    dim3 sgrid((p.W + 63) / 64, 2 * (p.C / 64), p.B * p.H);
+    dim3 sgrid(p.B * p.H, 2 * (p.C / 64), (p.W + 63) / 64);
     corr_tc_split_kernel<<<sgrid, 256, 0, st>>>(in1, in2, w, w + per, w + 2 * per, w + 3 * per, p.C, p.H, p.W);
     count_launch();
     return check_launch("correlation(tc split)");
