@@ -44,6 +44,12 @@ def install_pybind_extensions():
         spec = importlib.util.spec_from_file_location(name, path)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
+        if os.path.realpath(getattr(mod, "__file__", "")) != os.path.realpath(path):
+            # pybind11 caches extension modules by NAME per interpreter: if the reference's own `correlation_cuda` (or any
+            # other module of that name) was imported earlier in this process, a second load returns THAT module.
+            raise ImportError("a different extension module named %r is already loaded in this process (%s); the "
+                              "compiled modules of two implementations cannot coexist in one interpreter"
+                              % (name, getattr(mod, "__file__", "?")))
         sys.modules[name] = mod
 
 

@@ -127,16 +127,22 @@ def test_pybind_extension_modules_build_and_export_the_reference_interface():
     spec.loader.exec_module(bp)
     for so in bp.build():
         assert os.path.isfile(so)
-    from flownet2_b200 import compat
+    # in a child interpreter: pybind11 caches extension modules by name, and an earlier test of this process may have
+    # imported the reference's own correlation_cuda (oracle/_ref)
+    import subprocess
     import sys
-    compat.uninstall()
-    compat.install("B1p")
-    try:
-        for name in ("correlation_cuda", "resample2d_cuda", "channelnorm_cuda"):
-            mod = sys.modules[name]
-            assert mod.__file__.endswith(".so") and callable(mod.forward) and callable(mod.backward)
-        a = torch.zeros(1, 4, 8, 8)
-        with pytest.raises(RuntimeError):        # "input1 must be a CUDA tensor" (on a box without a driver c10 may
-            sys.modules["correlation_cuda"].forward(a, a, a.new(), a.new(), a.new(), 4, 1, 4, 1, 2, 1)   # replace the text)
-    finally:
-        compat.uninstall()
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from flownet2_b200 import compat\n"
+        "compat.install('B1p')\n"
+        "for name in ('correlation_cuda', 'resample2d_cuda', 'channelnorm_cuda'):\n"
+        "    mod = sys.modules[name]\n"
+        "    assert mod.__file__.endswith('.so') and '/pybind/' in mod.__file__ and callable(mod.forward) and callable(mod.backward)\n"
+        "a = torch.zeros(1, 4, 8, 8)\n"
+        "try:\n"
+        "    sys.modules['correlation_cuda'].forward(a, a, a.new(), a.new(), a.new(), 4, 1, 4, 1, 2, 1)\n"
+        "except RuntimeError as e:\n"
+        "    assert 'CUDA tensor' in str(e), str(e)\n"
+        "    print('OK')\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.stdout[-1000:], r.stderr[-2000:])

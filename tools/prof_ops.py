@@ -36,4 +36,11 @@ if what in ("small", "all"):
         F2.resample2d_backward(img, flow, go, out1=gi, out2=gf)
         F2.channelnorm_forward(img, out=n)
         F2.channelnorm_backward(img, n, gn, out=gi)
+    x = torch.rand(B, 6, H, W, device=dev, generator=g) - 0.5
+    lr = torch.randn(B, 2, H // 4, W // 4, device=dev, generator=g) * 0.2
+    cat = torch.empty(B, 12, H, W, device=dev)
+    gc = torch.randn(B, 12, H, W, device=dev, generator=g)
+    for _ in range(iters):
+        F2.warp_concat_forward(x, lr, upsample="bilinear", flow_mul=20.0, flow_div=20.0, out=cat)
+        F2.warp_concat_backward(x, flow, gc, flow_div=20.0)
 torch.cuda.synchronize()
