@@ -44,7 +44,10 @@ def build(force=False):
     from torch.utils import cpp_extension as ce
     inc = [INCLUDE, HERE] + ce.include_paths("cuda")
     libdirs = ce.library_paths("cuda")
-    cxx = os.environ.get("CXX", "g++")
+    # the system g++ (the one nvcc and torch's own extensions use), NOT $CXX: this image's $CXX is a private GCC whose
+    # libstdc++ is static-only -- linked into an extension it brings a second, uninitialised copy of the iostream locale
+    # machinery and the first integer formatted into an error message segfaults (found on the B200 box)
+    cxx = os.environ.get("FN2B200_CXX", "g++")
 
     def one(name):
         cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=" + name, "-DTORCH_API_INCLUDE_EXTENSION_H",
@@ -57,6 +60,9 @@ def build(force=False):
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError("building %s failed:\n%s" % (name, r.stdout[-4000:]))
+        syms = subprocess.run(["nm", "-D", "--defined-only", target(name) + ".tmp"], stdout=subprocess.PIPE, text=True).stdout
+        if "_ZNSo9_M_insert" in syms or "codecvt" in syms:
+            raise RuntimeError("%s: libstdc++ was linked statically into the extension (compiler %s); use the system g++" % (name, cxx))
         os.replace(target(name) + ".tmp", target(name))
         return target(name)
     with ThreadPoolExecutor(max_workers=3) as ex:

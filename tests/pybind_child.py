@@ -8,9 +8,11 @@ extension modules of the same names (oracle/_ref) -- the parent test computes wh
     python tests/pybind_child.py model <FlowNet2C|FlowNet2> <x.npy> <ref_out.npy>
 Prints one line starting with "OK" on success; any failure is an exception (non-zero exit).
 """
+import faulthandler
 import os
 import sys
 
+faulthandler.enable()
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
@@ -73,9 +75,11 @@ def ops():
     cn.forward(xh, nh, 2)                              # the reference dispatches on half too (channelnorm_kernel.cu:111)
     assert torch.allclose(nh.float(), no, atol=2e-3, rtol=2e-3)
     assert flownet2_b200.functional.launch_count() - n0 >= 9      # our library did the work
+    print("parity through the compiled modules: ok", flush=True)
     for bad, pat in ((lambda: cc.forward(a.cpu(), b.cpu(), r1, r2, out, 20, 1, 20, 1, 2, 1), "CUDA tensor"),
                      (lambda: cc.backward(a, b, r1, r2, go, g1, g2, 20, 1, 20, 2, 2, 1), "stride1"),
                      (lambda: rs.forward(img, flow, wo, 2, True), "kernel_size")):
+        print("expecting an error mentioning %r ..." % pat, flush=True)
         try:
             bad()
         except RuntimeError as e:
