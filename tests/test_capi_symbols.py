@@ -146,3 +146,41 @@ def test_pybind_extension_modules_build_and_export_the_reference_interface():
         "    print('OK')\n" % ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.stdout[-1000:], r.stderr[-2000:])
+
+
+def test_new_entry_points_validate_arguments_without_gpu():
+    """Round-2 entry points (fused warp-concat, upsampled-flow resample, correlation-into-concat, workspace queries):
+    argument errors are reported before anything touches the device."""
+    import flownet2_b200
+    L = flownet2_b200._lib.LIB
+    P, I64 = ctypes.c_void_p, ctypes.c_int64 * 4
+    st = I64(6 * 64, 64, 8, 1)
+    # empty batch is a no-op, not an error
+    assert L.fn2b200_warp_concat_forward(P(0), st, 3, P(0), 8, 8, 0, 1.0, P(0), 12, 0, 6, 6, 9, 20.0, -1, 11, 0, 8, 8, P(0)) != 0   # null flow
+    assert b"null flow" in L.fn2b200_last_error()
+    one = ctypes.c_float(0.0)
+    pf = ctypes.cast(ctypes.pointer(one), P)
+    assert L.fn2b200_warp_concat_forward(P(0), st, 3, pf, 8, 8, 0, 1.0, P(0), 12, 0, 6, 6, 9, 20.0, -1, 11, 0, 8, 8, P(0)) == 0      # B = 0
+    assert L.fn2b200_warp_concat_forward(P(0), st, 3, pf, 8, 8, 0, 1.0, P(0), 12, 0, 6, 4, 9, 20.0, -1, 11, 1, 8, 8, P(0)) == -1     # warped overlaps x
+    assert b"overlap" in L.fn2b200_last_error()
+    assert L.fn2b200_warp_concat_forward(P(0), st, 3, pf, 8, 8, 0, 1.0, P(0), 12, 0, 6, 6, 9, 0.0, -1, 11, 1, 8, 8, P(0)) == -1      # flow_div = 0
+    assert L.fn2b200_warp_concat_forward(P(0), st, 3, pf, 2, 3, 1, 1.0, P(0), 12, 0, 6, 6, 9, 20.0, -1, 11, 1, 8, 8, P(0)) == -1     # 4 * 3 != 8
+    assert b"does not match" in L.fn2b200_last_error()
+    assert L.fn2b200_warp_concat_forward(P(0), st, 3, pf, 8, 8, 3, 1.0, P(0), 12, 0, 6, 6, 9, 20.0, -1, 11, 1, 8, 8, P(0)) == -1     # bad mode
+    assert L.fn2b200_warp_concat_backward_workspace(2, 3, 8, 8) == 2 * 8 * 8 * 16
+    assert L.fn2b200_warp_concat_backward_workspace(2, 4, 8, 8) == 0
+    assert L.fn2b200_warp_concat_backward(P(0), st, 4, pf, pf, 12, 0, 6, 6, 9, 20.0, -1, 11, pf, pf, P(0), 0, 1, 8, 8, P(0)) == -2    # C > 3
+    assert L.fn2b200_resample2d_forward_up(P(0), st, pf, 2, 2, 1, 20.0, P(0), 0, 3, 8, 8, P(0)) == 0                              # B = 0
+    assert L.fn2b200_resample2d_forward_up(P(0), st, pf, 2, 2, 2, 20.0, P(0), 1, 3, 8, 12, P(0)) == -1                            # 4 * 2 != 12
+    # correlation into a concat buffer: the channel range must fit
+    assert L.fn2b200_correlation_forward_cat(pf, pf, pf, 440, 0, 0.1, 1, 64, 8, 8, 20, 1, 20, 1, 2, 1, P(0), 0, P(0)) == -1
+    assert b"do not fit" in L.fn2b200_last_error()
+    assert L.fn2b200_correlation_forward_cat(pf, pf, pf, 473, 32, 0.1, 0, 64, 8, 8, 20, 1, 20, 1, 2, 1, P(0), 0, P(0)) == 0        # B = 0
+    # Resample2d backward scratch: 16 bytes per image pixel for C <= 3, none for C > 3 or the planar scatter
+    assert L.fn2b200_resample2d_backward_workspace(st, 2, 3, 8, 8, 8, 8) == 2 * 8 * 8 * 16
+    assert L.fn2b200_resample2d_backward_workspace(st, 2, 5, 8, 8, 8, 8) == 0
+    os.environ["FN2B200_RS_BWD"] = "planar"
+    try:
+        assert L.fn2b200_resample2d_backward_workspace(st, 2, 3, 8, 8, 8, 8) == 0
+    finally:
+        del os.environ["FN2B200_RS_BWD"]
