@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark (contract in the task statement; layout in DESIGN.md section 5).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extras]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extras] [--step-path module|functional]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = Correlation forward + backward (both input gradients) at BASELINE.json configs[1]:
@@ -530,6 +530,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--flow-ref", nargs="+", metavar=("OUT_DIR", "MODEL"), help=argparse.SUPPRESS)
+    ap.add_argument("--step-path", default="module", choices=["module", "functional"],
+                    help="ours arm: time the nn.Module + autograd step (default, the call a user makes) or the functional C-ABI calls")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.flow_ref:                      # child of the ours arm: reference-kernel output flows for the agreement check
@@ -584,7 +586,7 @@ def main():
         if dist:
             dist.barrier()
 
-    if args.impl == "ours":
+    if args.impl == "ours" and args.step_path == "module":
         # the call a user makes: the nn.Module (autograd Function) forward, then backward of both input gradients;
         # the Function keeps the forward's bf16 hi/lo workspace for its backward
         import flownet2_b200
@@ -600,7 +602,8 @@ def main():
         def step():
             fwd(f1, f2, out)
             bwd(f1, f2, gO, g1, g2)
-        step_how = "correlation_cuda.forward + correlation_cuda.backward of the reference extension"
+        step_how = ("flownet2_b200.functional.correlation_forward + correlation_backward (workspace handed over)" if args.impl == "ours"
+                    else "correlation_cuda.forward + correlation_cuda.backward of the reference extension")
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -659,9 +662,12 @@ def main():
     e2e_check = float((hg1 - g1.cpu()).abs().max()) if args.impl == "ours" else 0.0   # same inputs -> same result as the resident step
 
     stats = torch.tensor([ms, ms_e / Ke * K], device=dev, dtype=torch.float64)
+    stats_min = stats.clone()
     if dist:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats_min, op=dist.ReduceOp.MIN)
     ms, ms_e_scaled = float(stats[0]), float(stats[1])
+    ms_fastest_rank = float(stats_min[0])
 
     # second half of BASELINE.json's metric: FlowNet2 image-pairs/sec (every rank runs a replica)
     flow = {}
@@ -737,6 +743,7 @@ def main():
         line = {
             "metric": "correlation_fwd_bwd_algorithmic_GBps", "value": round(value, 2), "unit": "GB/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 4),
+            "ms_per_step_fastest_rank": round(ms_fastest_rank / K, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "Correlation(pad=20,k=1,md=20,s1=1,s2=2) fwd+bwd on fp32 [8,256,112,256] per GPU "
                                    "(BASELINE configs[1])", "per_gpu_batch": B, "global_batch": B * world,
