@@ -149,6 +149,7 @@ __device__ __forceinline__ bool tc_next_seg(int &tn, int &w, int full, int w1, T
 constexpr int TC_MAXPROD = 4;
 constexpr int TC_EPIWARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPIWARPS + 32 * (TC_MAXPROD - 1);
+template <bool TS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ CUtensorMap m1l,
                    const __grid_constant__ CUtensorMap m2h, const __grid_constant__ CUtensorMap m2l,
@@ -159,6 +160,12 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
     const int Hc = H >> 1, Wc = W >> 1;
     const int nxt = (Wc + TC_TW - 1) / TC_TW, nyt = (Hc + TC_TH - 1) / TC_TH;
     const int nkb = C / TC_KB;
+    // TS: A_hi is copied from shared memory into tensor memory once per tile (tcgen05.cp, columns [288, 288 + C/2))
+    // and the hi x hi and hi x lo products read it from there (TS-mode MMA: 81.5 instead of 112.5 cycles per
+    // M128 x N144 x K16 MMA in isolation, tools/umma_rate.py); the 128 columns come out of the third accumulator buffer.
+    constexpr bool ts = TS;
+    constexpr int nacc = TS ? 2 : TC_NACC;
+    constexpr uint32_t TC_ATM = 2 * TC_N;          // first tensor-memory column of A_hi
     // Whole tiles round-robin over the CTAs (neighbouring tiles run concurrently and share their halos in L2;
     // contiguous per-CTA ranges were 50 % slower) for as many full rounds as there are; the tiles of the last,
     // partial round are dealt out by (tile, unit) pairs -- the 7 units of a tile write disjoint displacement
@@ -242,18 +249,31 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
             for (int tn = blockIdx.x, w = w0; tc_next_seg(tn, w, full, w1, sg); ++it) {
                 const int ua = sg.ua, ub = sg.ub;
                 for (int u = ua; u < ub; ++u, ++acount) {
-                    const int ab = acount % TC_NACC;
+                    const int ab = acount % nacc;
                     const bool rec = dbg && blockIdx.x == 0 && acount < 64 && lane == 0;
                     long long bwait = 0;
                     if (rec) dbg[acount * 8 + 0] = clock64();
-                    mbar_wait(&acc_empty[ab], ((acount / TC_NACC) & 1) ^ 1);
+                    mbar_wait(&acc_empty[ab], ((acount / nacc) & 1) ^ 1);
                     if (rec) dbg[acount * 8 + 1] = clock64();
                     tcgen05_fence_after();
                     const uint32_t d = tmem_base + ab * TC_N;
                     for (int kb = 0; kb < nkb; ++kb) {
-                        if (u == ua) mbar_wait(&a_full[kb], it & 1);
                         const uint64_t ah = umma_desc_k_sw128(smem_u32(sA + (0 * nkb + kb) * TC_ABLK));
                         const uint64_t al = umma_desc_k_sw128(smem_u32(sA + (1 * nkb + kb) * TC_ABLK));
+                        const uint32_t atm = tmem_base + TC_ATM + kb * (TC_KB / 2);
+                        if (u == ua) {
+                            mbar_wait(&a_full[kb], it & 1);
+                            if (ts) {
+                                // shared memory -> tensor memory, one K = 16 step per copy; ordered by issue with the
+                                // previous tile's MMAs that still read these columns and with the MMAs below
+                                tcgen05_fence_after();
+                                if (elect_one_sync()) {
+#pragma unroll
+                                    for (int ks = 0; ks < TC_KB / 16; ++ks) umma_cp_128x256b(atm + ks * 8, ah + 2 * ks);
+                                }
+                                __syncwarp();
+                            }
+                        }
                         for (int hl = 0; hl < 2; ++hl, ++bcount) {
                             const int s = bcount % TC_BST;
                             const long long tw0 = rec ? clock64() : 0;
@@ -265,13 +285,16 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
                                 if (hl == 0) {
 #pragma unroll
                                     for (int ks = 0; ks < TC_KB / 16; ++ks) {           // hi x hi, lo x hi
-                                        umma_bf16_ss(d, ah + 2 * ks, bd + 2 * ks, idesc, (kb | ks) != 0);
+                                        if (ts) umma_bf16_ts(d, atm + ks * 8, bd + 2 * ks, idesc, (kb | ks) != 0);
+                                        else umma_bf16_ss(d, ah + 2 * ks, bd + 2 * ks, idesc, (kb | ks) != 0);
                                         umma_bf16_ss(d, al + 2 * ks, bd + 2 * ks, idesc, 1);
                                     }
                                 } else {
 #pragma unroll
-                                    for (int ks = 0; ks < TC_KB / 16; ++ks)             // hi x lo
-                                        umma_bf16_ss(d, ah + 2 * ks, bd + 2 * ks, idesc, 1);
+                                    for (int ks = 0; ks < TC_KB / 16; ++ks) {           // hi x lo
+                                        if (ts) umma_bf16_ts(d, atm + ks * 8, bd + 2 * ks, idesc, 1);
+                                        else umma_bf16_ss(d, ah + 2 * ks, bd + 2 * ks, idesc, 1);
+                                    }
                                 }
                                 umma_commit(&b_empty[s]);                        // slot may be refilled
                                 if (hl == 1) {
@@ -312,10 +335,10 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
             const bool pix_ok = (yc < Hc) && (xc < Wc);
             float *obase = out + (long)T.n * out_bstride + (long)(2 * yc + T.py) * W + (2 * xc + T.px);
             for (int u = ua; u < ub; ++u, ++acount) {
-                const int ab = acount % TC_NACC;
+                const int ab = acount % nacc;
                 const bool rec = dbg && blockIdx.x == 0 && acount < 64 && p == 0 && half == 0;
                 if (rec) dbg[acount * 8 + 4] = clock64();
-                mbar_wait(&acc_full[ab], (acount / TC_NACC) & 1);
+                mbar_wait(&acc_full[ab], (acount / nacc) & 1);
                 if (rec) dbg[acount * 8 + 5] = clock64();
                 tcgen05_fence_after();
 #pragma unroll 1
@@ -758,7 +781,8 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrPa
     bst = tc_env_int("FN2B200_TC_BST", bst, 2, bst);
     const int hint = tc_env_int("FN2B200_TC_HINT", 1, 0, 1);
     const int smem = tc_smem_bytes(nkb, bst);
-    cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "correlation_forward(tc): smem attribute (%s)", cudaGetErrorString(e));
     const int grid = ntiles < sms ? ntiles : sms;
     // Producer-count rules (mbarrier parity waits only tell adjacent phases apart, so a producer must never be two
@@ -776,8 +800,13 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrPa
     while (nprod & (nprod - 1)) --nprod;          // power of two
     long long *dbg = nullptr;          // FN2B200_TC_DBG = device pointer: per-unit clock64 timeline of CTA 0 (tools/tc_timeline.py)
     if (const char *ev = getenv("FN2B200_TC_DBG")) dbg = reinterpret_cast<long long *>(strtoull(ev, nullptr, 0));
-    corr_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(m1h, m1l, m2h, m2l, out, p.out_bstride, p.leaky, p.B, p.C, p.H, p.W,
-                                                        ntiles, bst, hint, nprod, dbg);
+    const int ts = tc_env_int("FN2B200_TC_TS", 1, 0, 1);       // A_hi from tensor memory (TS-mode MMAs); 0 = all operands from shared memory
+    if (ts)
+        corr_fwd_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(m1h, m1l, m2h, m2l, out, p.out_bstride, p.leaky, p.B, p.C, p.H,
+                                                                  p.W, ntiles, bst, hint, nprod, dbg);
+    else
+        corr_fwd_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(m1h, m1l, m2h, m2l, out, p.out_bstride, p.leaky, p.B, p.C, p.H,
+                                                                   p.W, ntiles, bst, hint, nprod, dbg);
     count_launch();
     return check_launch("correlation_forward(tc)");
 }

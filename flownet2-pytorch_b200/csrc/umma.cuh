@@ -93,6 +93,13 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// shared memory -> tensor memory: 128 rows x 256 bits (32 bytes = one K = 16 bf16 step of a K-major operand) described by
+// the same matrix descriptor an SS-mode MMA would read, into 8 consecutive 32-bit columns of all 128 lanes starting at
+// taddr.  Issued by ONE thread; executes in issue order with the tcgen05.mma of the same thread (no barrier between a
+// copy and the MMAs that read it, nor between MMAs and a later copy that overwrites their operand).
+__device__ __forceinline__ void umma_cp_128x256b(uint32_t taddr, uint64_t smem_desc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(smem_desc) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                      smem_u32(bar))

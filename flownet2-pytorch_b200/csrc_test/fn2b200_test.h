@@ -25,6 +25,9 @@ int fn2b200_test_umma_gemm_mn(const void *A_bf16, const void *Bt_bf16, float *D,
 /* The _ss product with A read from tensor memory (written there with tcgen05.st); K = 64, 128, 192 or 256. */
 int fn2b200_test_umma_gemm_ts(const void *A_bf16, const void *B_bf16, float *D, int K, void *stream);
 
+/* The _ts product with A brought from shared memory (TMA, K-major SW128) into tensor memory by tcgen05.cp.128x256b. */
+int fn2b200_test_umma_gemm_tscp(const void *A_bf16, const void *B_bf16, float *D, int K, void *stream);
+
 /* MMA issue-rate benchmark: D[sm] = cycles per M128 x N x K16 bf16 MMA on that SM (D holds >= #SM floats).
  * mode 0 = A, B from shared memory (K-major), 1 = A from tensor memory, 2 = A, B MN-major. */
 int fn2b200_test_umma_rate(float *D, int mode, int N, int iters, void *stream);

@@ -6,6 +6,7 @@ namespace fn2 {
 int umma_selftest(const void *A, const void *B, float *D, int K, cudaStream_t st);
 int umma_selftest2(const void *A, const void *Bt, float *D, int a_sw32, cudaStream_t st);
 int umma_selftest_ts(const void *A, const void *B, float *D, int K, cudaStream_t st);
+int umma_selftest_tscp(const void *A, const void *B, float *D, int K, cudaStream_t st);
 int umma_rate_bench(float *out, int mode, int N, int iters, cudaStream_t st);
 int tma_feed_bench(const void *base, long long *out, int nimg, int C, int Hc, int Wc, int bw, int bh, int stages,
                    int per_stage, int iters, int grid, int cluster, int warps, cudaStream_t st);
@@ -31,6 +32,11 @@ int fn2b200_test_umma_gemm_ts(const void *A, const void *B, float *D, int K, voi
     if (!A || !B || !D) return fail(FN2B200_ENULL, "test_umma_gemm_ts: null pointer");
     if (int rc = bind_device_of(D)) return rc;
     return umma_selftest_ts(A, B, D, K, (cudaStream_t)stream);
+}
+int fn2b200_test_umma_gemm_tscp(const void *A, const void *B, float *D, int K, void *stream) {
+    if (!A || !B || !D) return fail(FN2B200_ENULL, "test_umma_gemm_tscp: null pointer");
+    if (int rc = bind_device_of(D)) return rc;
+    return umma_selftest_tscp(A, B, D, K, (cudaStream_t)stream);
 }
 int fn2b200_test_umma_rate(float *D, int mode, int N, int iters, void *stream) {
     if (!D) return fail(FN2B200_ENULL, "test_umma_rate: null pointer");

@@ -154,6 +154,80 @@ umma_selftest_ts_kernel(const __nv_bfloat16_raw *__restrict__ A, const __grid_co
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+// Variant TS-cp: A arrives in shared memory through TMA exactly as in variant 1 (K-major, 128-byte swizzle) and is copied
+// into tensor memory with tcgen05.cp.128x256b (one K = 16 step per copy) by the MMA-issuing thread, straight before the
+// TS-mode MMAs that read it -- the route the forward correlation kernel uses for its A_hi operand.
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_tscp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                          float *__restrict__ D, int K) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *sA = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [128 rows][128 B], SW128
+    unsigned char *sB = sA + ST_M * 128;                                                // [144 rows][128 B], SW128
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + ST_N * 128);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_tmem = tmem_base + 288;                      // columns [288, 288 + K/2): next to two 144-column accumulators
+    const uint32_t idesc = umma_idesc_bf16_f32(ST_M, ST_N);
+    const int nkb = K / ST_KB;
+    for (int kb = 0; kb < nkb; ++kb) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bars[0], (ST_M + ST_N) * 128);
+            tma_load_2d(sA, &mapA, &bars[0], kb * ST_KB, 0);
+            tma_load_2d(sB, &mapB, &bars[0], kb * ST_KB, 0);
+            mbar_wait(&bars[0], kb & 1);
+            tcgen05_fence_after();
+            const uint64_t da = umma_desc_k_sw128(smem_u32(sA)), db = umma_desc_k_sw128(smem_u32(sB));
+#pragma unroll
+            for (int ks = 0; ks < ST_KB / 16; ++ks) umma_cp_128x256b(a_tmem + (kb * ST_KB + ks * 16) / 2, da + 2 * ks);
+#pragma unroll
+            for (int ks = 0; ks < ST_KB / 16; ++ks)
+                umma_bf16_ts(tmem_base, a_tmem + (kb * ST_KB + ks * 16) / 2, db + 2 * ks, idesc, (kb | ks) != 0);
+            umma_commit(&bars[1]);
+            mbar_wait(&bars[1], kb & 1);
+        }
+        __syncthreads();
+    }
+    tcgen05_fence_after();
+    for (int c0 = 0; c0 < ST_N; c0 += 16) {
+        float r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) D[tid * ST_N + c0 + j] = r[j];
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+int umma_selftest_tscp(const void *A, const void *B, float *D, int K, cudaStream_t st) {
+    if (K <= 0 || K % ST_KB || K > 256) return fail(FN2B200_EINVAL, "umma_selftest_tscp: K must be 64, 128, 192 or 256");
+    CUtensorMap ma, mb;
+    uint64_t dimsA[2] = {(uint64_t)K, ST_M}, dimsB[2] = {(uint64_t)K, ST_N};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t boxA[2] = {ST_KB, ST_M}, boxB[2] = {ST_KB, ST_N};
+    int rc = make_tensor_map_bf16_sw128(&ma, A, 2, dimsA, str, boxA);
+    if (rc) return rc;
+    rc = make_tensor_map_bf16_sw128(&mb, B, 2, dimsB, str, boxB);
+    if (rc) return rc;
+    const int smem = (ST_M + ST_N) * 128 + 1024 + 64;
+    cudaError_t e = cudaFuncSetAttribute(umma_selftest_tscp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail((int)e, "umma_selftest_tscp: smem attribute (%s)", cudaGetErrorString(e));
+    umma_selftest_tscp_kernel<<<1, 128, smem, st>>>(ma, mb, D, K);
+    count_launch();
+    return check_launch("umma_selftest_tscp");
+}
+
 int umma_selftest_ts(const void *A, const void *B, float *D, int K, cudaStream_t st) {
     if (K <= 0 || K % ST_KB || K > 256) return fail(FN2B200_EINVAL, "umma_selftest_ts: K must be 64, 128, 192 or 256");
     CUtensorMap mb;

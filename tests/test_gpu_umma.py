@@ -64,3 +64,22 @@ def test_umma_gemm_a_from_tensor_memory(K):
     ref = A.double() @ B.double().t()
     err = (D.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("K", [64, 256])
+def test_umma_gemm_a_copied_to_tensor_memory_by_tcgen05_cp(K):
+    """TS mode with A staged shared memory -> tensor memory by tcgen05.cp.128x256b (the forward kernel's A_hi route)."""
+    import testlib
+    LIB = testlib.load()
+    g = torch.Generator().manual_seed(200 + K)
+    A = torch.randn(128, K, generator=g).bfloat16()
+    B = torch.randn(144, K, generator=g).bfloat16()
+    Ad, Bd = A.cuda(), B.cuda()
+    D = torch.full((128, 144), float("nan"), device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    testlib.check(LIB, LIB.fn2b200_test_umma_gemm_tscp(ctypes.c_void_p(Ad.data_ptr()), ctypes.c_void_p(Bd.data_ptr()),
+                                                       ctypes.c_void_p(D.data_ptr()), K, st), "test_umma_gemm_tscp")
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t()
+    err = (D.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err

@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(ROOT, "flownet2-pytorch_b200", "libfn2b200_test.so")
 HEADER = os.path.join(ROOT, "flownet2-pytorch_b200", "csrc_test", "fn2b200_test.h")
 
 SYMBOLS = ("fn2b200_test_last_error", "fn2b200_test_umma_gemm_ss", "fn2b200_test_umma_gemm_mn", "fn2b200_test_umma_gemm_ts",
-           "fn2b200_test_umma_rate", "fn2b200_test_tma_feed", "fn2b200_test_atomics_bench")
+           "fn2b200_test_umma_gemm_tscp", "fn2b200_test_umma_rate", "fn2b200_test_tma_feed", "fn2b200_test_atomics_bench")
 
 
 def load():
@@ -20,6 +20,7 @@ def load():
     lib.fn2b200_test_umma_gemm_ss.argtypes = [p, p, p, i, p]
     lib.fn2b200_test_umma_gemm_mn.argtypes = [p, p, p, i, p]
     lib.fn2b200_test_umma_gemm_ts.argtypes = [p, p, p, i, p]
+    lib.fn2b200_test_umma_gemm_tscp.argtypes = [p, p, p, i, p]
     lib.fn2b200_test_umma_rate.argtypes = [p, i, i, i, p]
     lib.fn2b200_test_tma_feed.argtypes = [p, p] + [i] * 12 + [p]
     lib.fn2b200_test_atomics_bench.argtypes = [p, p, i, i, i, i, p]
