@@ -44,8 +44,10 @@ constexpr int TC_ABLK = 128 * 128;             // bytes of one A k-block (128 ro
 constexpr int TC_BBLK = TC_N * 128;            // bytes of one B k-block (144 rows x 128 B)
 constexpr int TC_NBAR = 2 * TC_MAXKB + 2 * TC_MAXBST + 2 * TC_NACC;
 constexpr int TC_SMEM_MAX = 232448;                        // 227 KB opt-in limit per CTA
-__host__ __device__ constexpr int tc_smem_bytes(int nkb, int bst) {
-    return 2 * nkb * TC_ABLK + bst * TC_BBLK + TC_NBAR * 8 + 16 + 1024;   // bst slots of one box
+// dedicated A blocks: hi and lo (SS mode) or lo only (TS mode: the A_hi blocks pass through the B ring on their way
+// to tensor memory), then bst ring slots of one 18-KB box each
+__host__ __device__ constexpr int tc_smem_bytes(int nkb, int bst, bool ts = false) {
+    return (ts ? 1 : 2) * nkb * TC_ABLK + bst * TC_BBLK + TC_NBAR * 8 + 16 + 1024;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -175,8 +177,12 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
     const int w0 = (int)blockIdx.x * wper < wtotal ? (int)blockIdx.x * wper : wtotal;
     const int w1 = (w0 + wper < wtotal) ? w0 + wper : wtotal;
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char *sA = smem;                                   // [hl][kb][128 x 128 B]
-    unsigned char *sB = smem + 2 * nkb * TC_ABLK;               // [slot][144 x 128 B]
+    // SS: sA = [hi | lo][kb][128 x 128 B].  TS: sA = [lo][kb][128 x 128 B] only -- an A_hi block is needed in shared memory
+    // just long enough to be copied into tensor memory, so it travels through a ring slot like a B stage (16 KB of
+    // the slot's 18 KB), which leaves room for 8 ring slots instead of 5 (1 unit of look-ahead instead of 0.6).
+    unsigned char *sA = smem;
+    unsigned char *sAlo = smem + (TS ? 0 : nkb * TC_ABLK);
+    unsigned char *sB = smem + (TS ? 1 : 2) * nkb * TC_ABLK;    // [slot][144 x 128 B]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TC_BST * TC_BBLK);
     uint64_t *a_full = bars, *a_empty = bars + TC_MAXKB;
     uint64_t *b_full = bars + 2 * TC_MAXKB, *b_empty = b_full + TC_MAXBST;
@@ -213,13 +219,26 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
                 const int ua = sg.ua, ub = sg.ub;
                 const TcTile T = tc_decode(sg.t, nxt, nyt);
                 const int img = T.n * 4 + T.py * 2 + T.px;
+                if (TS) {
+                    // the tile's A_hi blocks as ring stages (consumed by tcgen05.cp, first thing in the segment)
+                    for (int kb = 0; kb < nkb; ++kb, ++bcount, ++job) {
+                        if ((int)(job % (uint32_t)nprod) != prod) continue;
+                        const int s = bcount % TC_BST;
+                        mbar_wait(&b_empty[s], ((bcount / TC_BST) & 1) ^ 1);
+                        if (elect_one_sync()) {
+                            mbar_arrive_expect_tx(&b_full[s], TC_ABLK);
+                            load(sB + s * TC_BBLK, &m1h, &b_full[s], kb * TC_KB, T.xc0, T.yc0, img);
+                        }
+                        __syncwarp();
+                    }
+                }
                 for (int kb = 0; kb < nkb; ++kb, ++job) {
                     if ((int)(job % (uint32_t)nprod) != prod) continue;
                     mbar_wait(&a_empty[kb], (it & 1) ^ 1);
                     if (elect_one_sync()) {
-                        mbar_arrive_expect_tx(&a_full[kb], 2 * TC_ABLK);
-                        load(sA + (0 * nkb + kb) * TC_ABLK, &m1h, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
-                        load(sA + (1 * nkb + kb) * TC_ABLK, &m1l, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
+                        mbar_arrive_expect_tx(&a_full[kb], (TS ? 1 : 2) * TC_ABLK);
+                        if (!TS) load(sA + kb * TC_ABLK, &m1h, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
+                        load(sAlo + kb * TC_ABLK, &m1l, &a_full[kb], kb * TC_KB, T.xc0, T.yc0, img);
                     }
                     __syncwarp();
                 }
@@ -248,6 +267,24 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
             TcSeg sg;
             for (int tn = blockIdx.x, w = w0; tc_next_seg(tn, w, full, w1, sg); ++it) {
                 const int ua = sg.ua, ub = sg.ub;
+                if (TS) {
+                    // A_hi: ring stage -> tensor memory, one K = 16 step per copy.  tcgen05.cp and tcgen05.mma execute in
+                    // issue order: the copies wait for the previous tile's MMAs that still read these columns, the MMAs
+                    // below wait for the copies; the commit frees the ring slot once the copies have read it.
+                    for (int kb = 0; kb < nkb; ++kb, ++bcount) {
+                        const int s = bcount % TC_BST;
+                        mbar_wait(&b_full[s], (bcount / TC_BST) & 1);
+                        tcgen05_fence_after();
+                        if (elect_one_sync()) {
+                            const uint64_t src = umma_desc_k_sw128(smem_u32(sB + s * TC_BBLK));
+                            const uint32_t dst = tmem_base + TC_ATM + kb * (TC_KB / 2);
+#pragma unroll
+                            for (int ks = 0; ks < TC_KB / 16; ++ks) umma_cp_128x256b(dst + ks * 8, src + 2 * ks);
+                            umma_commit(&b_empty[s]);
+                        }
+                        __syncwarp();
+                    }
+                }
                 for (int u = ua; u < ub; ++u, ++acount) {
                     const int ab = acount % nacc;
                     const bool rec = dbg && blockIdx.x == 0 && acount < 64 && lane == 0;
@@ -258,22 +295,10 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constan
                     tcgen05_fence_after();
                     const uint32_t d = tmem_base + ab * TC_N;
                     for (int kb = 0; kb < nkb; ++kb) {
-                        const uint64_t ah = umma_desc_k_sw128(smem_u32(sA + (0 * nkb + kb) * TC_ABLK));
-                        const uint64_t al = umma_desc_k_sw128(smem_u32(sA + (1 * nkb + kb) * TC_ABLK));
+                        const uint64_t ah = umma_desc_k_sw128(smem_u32(sA + kb * TC_ABLK));          // SS mode only
+                        const uint64_t al = umma_desc_k_sw128(smem_u32(sAlo + kb * TC_ABLK));
                         const uint32_t atm = tmem_base + TC_ATM + kb * (TC_KB / 2);
-                        if (u == ua) {
-                            mbar_wait(&a_full[kb], it & 1);
-                            if (ts) {
-                                // shared memory -> tensor memory, one K = 16 step per copy; ordered by issue with the
-                                // previous tile's MMAs that still read these columns and with the MMAs below
-                                tcgen05_fence_after();
-                                if (elect_one_sync()) {
-#pragma unroll
-                                    for (int ks = 0; ks < TC_KB / 16; ++ks) umma_cp_128x256b(atm + ks * 8, ah + 2 * ks);
-                                }
-                                __syncwarp();
-                            }
-                        }
+                        if (u == ua) mbar_wait(&a_full[kb], it & 1);
                         for (int hl = 0; hl < 2; ++hl, ++bcount) {
                             const int s = bcount % TC_BST;
                             const long long tw0 = rec ? clock64() : 0;
@@ -776,11 +801,12 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrPa
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nkb = p.C / TC_KB;
+    const int ts = tc_env_int("FN2B200_TC_TS", 1, 0, 1);       // A_hi from tensor memory (TS-mode MMAs); 0 = all operands from shared memory
     int bst = 2;
-    while (bst < TC_MAXBST && tc_smem_bytes(nkb, bst + 1) <= TC_SMEM_MAX) ++bst;
+    while (bst < TC_MAXBST && tc_smem_bytes(nkb, bst + 1, ts) <= TC_SMEM_MAX) ++bst;
     bst = tc_env_int("FN2B200_TC_BST", bst, 2, bst);
     const int hint = tc_env_int("FN2B200_TC_HINT", 1, 0, 1);
-    const int smem = tc_smem_bytes(nkb, bst);
+    const int smem = tc_smem_bytes(nkb, bst, ts);
     cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "correlation_forward(tc): smem attribute (%s)", cudaGetErrorString(e));
@@ -800,7 +826,6 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, const CorrPa
     while (nprod & (nprod - 1)) --nprod;          // power of two
     long long *dbg = nullptr;          // FN2B200_TC_DBG = device pointer: per-unit clock64 timeline of CTA 0 (tools/tc_timeline.py)
     if (const char *ev = getenv("FN2B200_TC_DBG")) dbg = reinterpret_cast<long long *>(strtoull(ev, nullptr, 0));
-    const int ts = tc_env_int("FN2B200_TC_TS", 1, 0, 1);       // A_hi from tensor memory (TS-mode MMAs); 0 = all operands from shared memory
     if (ts)
         corr_fwd_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(m1h, m1l, m2h, m2l, out, p.out_bstride, p.leaky, p.B, p.C, p.H,
                                                                   p.W, ntiles, bst, hint, nprod, dbg);
