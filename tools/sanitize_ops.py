@@ -85,6 +85,13 @@ if which in ("fused", "all"):
     lr = torch.randn(2, 2, 6, 10, generator=g) * 0.3
     cat = F2.warp_concat_forward(x.to(dev), lr.to(dev), upsample="bilinear", flow_mul=20.0, flow_div=20.0)
     errs["fused_fwd"] = rel(cat, orc.warp_concat_forward(x.numpy(), lr.numpy(), upsample_mode=1, flow_mul=20.0, flow_div=20.0))
+    fl = torch.randn(2, 2, 24, 40, generator=g) * 3
+    gc = torch.randn(2, 12, 24, 40, generator=g)
+    gx, gf = F2.warp_concat_backward(x.to(dev), fl.to(dev), gc.to(dev), flow_div=20.0)
+    rx, rf = orc.warp_concat_backward(x.numpy(), fl.numpy(), gc.numpy(), flow_div=20.0)
+    errs["fused_bwd_gx"], errs["fused_bwd_gflow"] = rel(gx, rx), rel(gf, rf)
+    up = F2.resample2d_forward_up(x[:, 3:].to(dev), lr.to(dev), "nearest", 20.0)
+    errs["resample_up"] = rel(up, orc.resample2d_forward(np.ascontiguousarray(x[:, 3:].numpy()), orc.upsample4(lr.numpy(), 2, 20.0)))
     a, b = rnd((1, 64, 12, 20), 12), rnd((1, 64, 12, 20), 13)
     buf = torch.zeros(1, 32 + 441, 12, 20, device=dev)
     F2.correlation_forward_cat(a.to(dev), b.to(dev), buf, 32, 0.1, 20, 1, 20, 1, 2)
