@@ -37,6 +37,11 @@ def install_pybind_extensions():
     import sysconfig
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pybind")
     suffix = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
+    if not all(os.path.isfile(os.path.join(here, n + suffix)) for n in _EXT) and os.environ.get("FN2B200_AUTOBUILD", "1") == "1":
+        spec = importlib.util.spec_from_file_location("_fn2b200_build_pybind", os.path.join(here, "build_pybind.py"))
+        bp = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bp)
+        bp.build()                      # g++ only, ~40 s; like libfn2b200.so the modules are built in-tree on first use
     for name in _EXT:
         path = os.path.join(here, name + suffix)
         if not os.path.isfile(path):
