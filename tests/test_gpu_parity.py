@@ -126,6 +126,25 @@ def test_correlation_tc_partial_last_round_and_producer_counts(monkeypatch):
     monkeypatch.delenv("FN2B200_TC_NP")
 
 
+def test_correlation_tc_more_than_65535_rows(monkeypatch):
+    """B * H > 65535: the split prepass carries (sample, row) in grid x (grid z was capped at 65535 and the
+    default tensor-core path failed with 'invalid configuration').  Checked against the FP32-FMA kernels."""
+    f = _f2()
+    shape = (1200, 64, 56, 16)                          # 67200 rows
+    assert f._lib.LIB.fn2b200_correlation_path(shape[1], shape[2], shape[3], 20, 1, 20, 1, 2) == 2
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(*shape, device="cuda", generator=g)
+    b = torch.randn(*shape, device="cuda", generator=g)
+    out = f.functional.correlation_forward(a, b, 20, 1, 20, 1, 2)
+    monkeypatch.setenv("FN2B200_CORR_FWD", "fma")
+    ref = f.functional.correlation_forward(a, b, 20, 1, 20, 1, 2)
+    monkeypatch.delenv("FN2B200_CORR_FWD")
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 5e-5
+    n = 1199
+    o1 = orc.correlation_forward(a[n:n + 1].cpu().numpy(), b[n:n + 1].cpu().numpy(), 20, 1, 20, 1, 2)
+    assert_close(out[n:n + 1].cpu().numpy(), o1, TOL, "last sample of 1200")
+
+
 def test_correlation_stride1_2_forward_only():
     f = _f2()
     a, b = _randn((1, 4, 12, 13), 1), _randn((1, 4, 12, 13), 2)
