@@ -67,8 +67,12 @@ def _corr_module(net_c):
 
 def flownetc_forward(net_c, x):
     """networks/FlowNetC.py:70-126 in eval mode -> (flow2,).  x: [B,6,H,W]."""
+    return _flownetc_pair(net_c, x[:, 0:3], x[:, 3:])
+
+
+def _flownetc_pair(net_c, x1, x2):
+    """FlowNetC on the two frames given separately (FlowNet2C feeds x[:,:,0] and x[:,:,1], models.py:192-194)."""
     with torch.no_grad():
-        x1, x2 = x[:, 0:3], x[:, 3:]
         out_conv1a = net_c.conv1(x1)
         out_conv2a = net_c.conv2(out_conv1a)
         out_conv3a = net_c.conv3(out_conv2a)
@@ -79,7 +83,7 @@ def flownetc_forward(net_c, x):
         D, oH, oW = F2.correlation_out_shape(C, H, W, corr.pad_size, corr.kernel_size, corr.max_displacement, corr.stride1,
                                              corr.stride2)
         nredir = out_conv_redir.size(1)
-        in_conv3_1 = torch.empty((B, nredir + D, oH, oW), dtype=torch.float32, device=x.device)
+        in_conv3_1 = torch.empty((B, nredir + D, oH, oW), dtype=torch.float32, device=x1.device)
         in_conv3_1[:, :nredir].copy_(out_conv_redir)
         F2.correlation_forward_cat(out_conv3a, out_conv3b, in_conv3_1, nredir, net_c.corr_activation.negative_slope,
                                    corr.pad_size, corr.kernel_size, corr.max_displacement, corr.stride1, corr.stride2,
@@ -109,8 +113,7 @@ def flownet2c_forward(net, inputs):
     """models.FlowNet2C.forward (models.py:189-243) in eval mode: upsample1(flow2 * div_flow)."""
     with torch.no_grad():
         x = _normalise(inputs, net.rgb_max)
-        x = torch.cat((x[:, :, 0], x[:, :, 1]), dim=1)
-        flow2 = flownetc_forward(net, x)[0]
+        flow2 = _flownetc_pair(net, x[:, :, 0], x[:, :, 1])[0]
         return net.upsample1(flow2 * net.div_flow)
 
 
