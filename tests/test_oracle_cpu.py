@@ -158,3 +158,52 @@ def test_oracle_matches_reference_kernel_golden(path):
                      "golden cnorm bwd")
     else:
         raise AssertionError(op)
+
+
+def test_upsample4_matches_torch_interpolate():
+    """orc_upsample4 restates nn.Upsample(scale_factor=4) (models.py:42,56,72-73); pinned against torch on CPU."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    f = torch.randn(2, 2, 7, 9, generator=g)
+    for mode, name, tol in ((1, "bilinear", 1e-6), (2, "nearest", 0.0)):
+        ref = torch.nn.Upsample(scale_factor=4, mode=name)(f * 20.0).numpy()
+        out = orc.upsample4(f.numpy(), mode, 20.0)
+        assert out.shape == ref.shape
+        assert np.abs(out - ref).max() <= tol * np.abs(ref).max()
+    import pytest
+    with pytest.raises(ValueError):
+        orc.upsample4(f.numpy(), 3)
+
+
+def test_warp_concat_compositions_against_fp64_autograd():
+    """The oracle's compositions for the fused warp -> diff -> norm -> concat op (forward and backward) against an
+    independent fp64 formulation: grid_sample(border, align_corners=True) is Resample2d's bilinear warp for in-range and
+    clamped samples alike (SURVEY R-2), the rest is plain torch."""
+    import torch
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(1, 6, 12, 16, generator=g) - 0.5
+    fl = torch.randn(1, 2, 12, 16, generator=g) * 2
+    gc = torch.randn(1, 12, 12, 16, generator=g)
+    cat = orc.warp_concat_forward(x.numpy(), fl.numpy(), flow_div=20.0)
+    rx, rf = orc.warp_concat_backward(x.numpy(), fl.numpy(), gc.numpy(), flow_div=20.0)
+    xd, fd = x.double().requires_grad_(), fl.double().requires_grad_()
+    H, W = 12, 16
+    yy, xx = torch.meshgrid(torch.arange(H).double(), torch.arange(W).double(), indexing="ij")
+    gx = (xx + fd[:, 0]) / (W - 1) * 2 - 1
+    gy = (yy + fd[:, 1]) / (H - 1) * 2 - 1
+    warped = torch.nn.functional.grid_sample(xd[:, 3:], torch.stack((gx, gy), -1), mode="bilinear", padding_mode="border",
+                                             align_corners=True)
+    diff = xd[:, :3] - warped
+    ref = torch.cat((xd, warped, fd / 20.0, diff.pow(2).sum(1, keepdim=True).sqrt()), 1)
+    assert np.abs(cat - ref.detach().numpy()).max() < 1e-5
+    ref.backward(gc.double())
+    assert np.abs(rx - xd.grad.numpy()).max() < 1e-5 * max(1.0, np.abs(rx).max())
+    assert np.abs(rf - fd.grad.numpy()).max() < 1e-5 * max(1.0, np.abs(rf).max())
+    # the fusion-stage layout: quarter-resolution flow, nearest upsample, flow + its norm + the diff norm
+    lr = torch.randn(1, 2, 3, 4, generator=g)
+    c3 = orc.warp_concat_forward(x.numpy(), lr.numpy(), upsample_mode=2, flow_mul=0.05, cat_channels=11, ch_x=0, n_x=3,
+                                 ch_warped=-1, ch_flow=3, flow_div=1.0, ch_flow_norm=7, ch_diff_norm=9)
+    up = torch.nn.Upsample(scale_factor=4, mode="nearest")(lr * 0.05)
+    assert np.abs(c3[:, 3:5] - up.numpy()).max() < 1e-7
+    assert np.abs(c3[:, 7] - up.pow(2).sum(1).sqrt().numpy()).max() < 1e-6
+    assert (c3[:, 5:7] == 0).all() and (c3[:, 8] == 0).all() and (c3[:, 10] == 0).all()
